@@ -1,0 +1,123 @@
+/* TEST INFRASTRUCTURE ONLY — see oracle.h for scope and pinning status.
+ *
+ * Matrix-vector side of the oracle.  The reference's mv/ driver (mv/mv.c) calls four MKL CBLAS level-2
+ * routines on a dense buffer; MKL is third-party and absent, so each routine is restated here from its
+ * published BLAS definition, with the exact argument choices of the reference call sites. */
+#include "oracle.h"
+
+#include <math.h>
+#include <omp.h>
+#include <stdlib.h>
+#include <string.h>
+
+int oracle_omp_max_threads(void) { return omp_get_max_threads(); }
+
+/* y = A x on the reference's CSR container (mm/inc/CSR.h:22-100: 0-based rowptr[rows+1], colids, values),
+ * alpha = 1, beta = 0 as every call in mv/mv.c:6-27.  One left-to-right sum per row, separate multiply
+ * and add (built with -ffp-contract=off), so the result is a fixed function of the stored order. */
+void oracle_spmv_csr(int rows, const int *rowptr, const int *colids, const double *values, const double *x,
+                     double *y) {
+    for (int i = 0; i < rows; ++i) {
+        double s = 0.0;
+        for (long j = rowptr[i]; j < rowptr[i + 1]; ++j) s += values[j] * x[colids[j]];
+        y[i] = s;
+    }
+}
+
+/* Same product, rows split over OpenMP threads (each row still summed left to right, so the result is
+ * bit-identical to oracle_spmv_csr).  This is the CPU baseline bench.py times. */
+void oracle_spmv_csr_omp(int rows, const int *rowptr, const int *colids, const double *values, const double *x,
+                         double *y) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < rows; ++i) {
+        double s = 0.0;
+        for (long j = rowptr[i]; j < rowptr[i + 1]; ++j) s += values[j] * x[colids[j]];
+        y[i] = s;
+    }
+}
+
+/* sum_j |a_ij| |x_j| : the scale against which tests state the 1e-12 relative tolerance. */
+void oracle_spmv_csr_abs(int rows, const int *rowptr, const int *colids, const double *values, const double *x,
+                         double *yabs) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < rows; ++i) {
+        double s = 0.0;
+        for (long j = rowptr[i]; j < rowptr[i + 1]; ++j) s += fabs(values[j]) * fabs(x[colids[j]]);
+        yabs[i] = s;
+    }
+}
+
+/* mv/mv.c:23-27  cblas_dgemv(ColMajor, NoTrans, dim, dim, 1.0, A, dim, B, 1, 0.0, C, 1).
+ * Column-major element (i,j) = A[i + j*dim]; the driver filled A row-major (mv/mv.c:62), so this is
+ * y = (file matrix)^T x. */
+void oracle_dgemv(const double *A, const double *B, double *C, int dim) {
+    for (int i = 0; i < dim; ++i) C[i] = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        const double xj = B[j];
+        const double *col = A + (size_t)j * dim;
+        for (int i = 0; i < dim; ++i) C[i] += col[i] * xj;
+    }
+}
+
+/* mv/mv.c:6-10  cblas_dsymv(ColMajor, Upper, dim, 1.0, A, dim, B, 1, 0.0, C, 1).
+ * Only a(i,j), i <= j, = A[i + j*dim] is referenced; the strictly lower part is its mirror. */
+void oracle_dsymv(const double *A, const double *B, double *C, int dim) {
+    for (int i = 0; i < dim; ++i) C[i] = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        const double *col = A + (size_t)j * dim;
+        double t = 0.0;
+        for (int i = 0; i < j; ++i) {
+            C[i] += col[i] * B[j];
+            t += col[i] * B[i];
+        }
+        C[j] += col[j] * B[j] + t;
+    }
+}
+
+/* mv/mv.c:12-15  cblas_dtrmv(ColMajor, Upper, Trans, NonUnit, dim, A, dim, B, 1):  B <- U^T B in place,
+ * U(i,j) = A[i + j*dim] for i <= j.  C is not touched. */
+void oracle_dtrmv(const double *A, double *B, double *C, int dim) {
+    (void)C;
+    for (int j = dim - 1; j >= 0; --j) { /* descending j only reads B[i], i <= j: safe in place */
+        const double *col = A + (size_t)j * dim;
+        double t = 0.0;
+        for (int i = 0; i <= j; ++i) t += col[i] * B[i];
+        B[j] = t;
+    }
+}
+
+/* mv/mv.c:17-21  cblas_dspmv(ColMajor, Upper, dim, 1.0, A, B, 1, 0.0, C, 1): the dense buffer is read AS IF
+ * it were packed-upper storage: a(i,j), i <= j, = A[i + j(j+1)/2] (first dim(dim+1)/2 doubles). */
+void oracle_dspmv(const double *A, const double *B, double *C, int dim) {
+    for (int i = 0; i < dim; ++i) C[i] = 0.0;
+    for (int j = 0; j < dim; ++j) {
+        const double *col = A + (size_t)j * (j + 1) / 2;
+        double t = 0.0;
+        for (int i = 0; i < j; ++i) {
+            C[i] += col[i] * B[j];
+            t += col[i] * B[i];
+        }
+        C[j] += col[j] * B[j] + t;
+    }
+}
+
+/* Block-CSR (bs x bs row-major blocks) times a row-major dense block of ncol columns.  There is no such
+ * routine in the reference; this restates C = A B for BASELINE config 5 so the
+ * tensor-core path has a checker.  PARITY UNPINNED. */
+void oracle_bsr_spmm(int mb, int bs, const int *browptr, const int *bcolids, const double *bvalues, int ncol,
+                     const double *B, double *C) {
+#pragma omp parallel for schedule(static)
+    for (int I = 0; I < mb; ++I) {
+        double *crow = C + (size_t)I * bs * ncol;
+        memset(crow, 0, sizeof(double) * bs * ncol);
+        for (long p = browptr[I]; p < browptr[I + 1]; ++p) {
+            const double *blk = bvalues + (size_t)p * bs * bs;
+            const double *brow = B + (size_t)bcolids[p] * bs * ncol;
+            for (int r = 0; r < bs; ++r)
+                for (int s = 0; s < bs; ++s) {
+                    const double a = blk[r * bs + s];
+                    for (int c = 0; c < ncol; ++c) crow[r * ncol + c] += a * brow[s * ncol + c];
+                }
+        }
+    }
+}
