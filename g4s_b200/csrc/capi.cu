@@ -1,0 +1,304 @@
+// C-ABI glue: error state, device checks, CSR handles, SpMV entry points, Timings, partitioner.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace g4s {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+int fail(int status, const std::string &msg) {
+    t_error = msg;
+    return status;
+}
+
+static int g_sm_count[64];
+static int g_dev_ok[64];
+
+int ensure_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(G4S_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (dev < 0 || dev >= 64) return fail(G4S_ERR_CUDA, "device ordinal out of range");
+    if (g_dev_ok[dev] == 1) return G4S_OK;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(G4S_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(G4S_ERR_CUDA, "g4s_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor) + " (there is no fallback path)");
+    g_sm_count[dev] = prop.multiProcessorCount;
+    g_dev_ok[dev] = 1;
+    return G4S_OK;
+}
+
+int sm_count() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) ? g_sm_count[dev] : 148;
+}
+
+int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream);
+int spmv_build_plan(g4s_csr *h, cudaStream_t stream);
+void spmv_free_plan(g4s_csr *h);
+
+// Device arrays carry 64 bytes of slack so that 16-byte bulk copies may round the last element up.
+int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz) {
+    g4s_csr *h = new (std::nothrow) g4s_csr();
+    if (!h) return fail(G4S_ERR_ALLOC, "host allocation failed");
+    h->rows = rows;
+    h->cols = cols;
+    h->nnz = nnz;
+    h->owns = true;
+    cudaError_t e = cudaMalloc(&h->rowptr, sizeof(int) * ((size_t)rows + 1) + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&h->colids, sizeof(int) * (size_t)nnz + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&h->values, sizeof(double) * (size_t)nnz + 64);
+    if (e != cudaSuccess) {
+        g4s_csr_destroy(h);
+        return fail(G4S_ERR_ALLOC, std::string("cudaMalloc CSR: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return G4S_OK;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace g4s
+
+// ---- partitioner (BIN::set_rows_offset, mm/inc/BIN.h:100-122) ------------------------------------------
+template <class T>
+static int partition_rows(const T *prefix, int rows, int parts, int *cuts) {
+    if (!prefix || !cuts || rows < 0 || parts < 1) return g4s::fail(G4S_ERR_INVALID, "g4s_partition_rows: bad arguments");
+    const long long total = (long long)prefix[rows] - (long long)prefix[0];
+    const long long avg = (total + parts - 1) / parts;
+    cuts[0] = 0;
+    for (int p = 0; p < parts; ++p) {
+        const long long target = (long long)prefix[0] + avg * (p + 1);
+        const T *it = std::lower_bound(prefix, prefix + rows + 1, target,
+                                       [](const T &a, long long b) { return (long long)a < b; });
+        long long idx = it - prefix;
+        cuts[p + 1] = (int)std::min<long long>(idx, rows);
+    }
+    cuts[parts] = rows;
+    return G4S_OK;
+}
+using namespace g4s;
+
+extern "C" {
+
+const char *g4s_last_error(void) { return t_error.c_str(); }
+const char *g4s_version(void) { return "g4s_b200 0.1 (sm_100a)"; }
+long long g4s_kernel_launch_count(void) { return g_launches.load(); }
+
+int g4s_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int g4s_set_device(int device) {
+    G4S_CUDA(cudaSetDevice(device));
+    return ensure_device();
+}
+
+// ---- Timings (mm/src/Timings.cpp) -----------------------------------------------------------------------
+void g4s_timings_init(g4s_timings *t) {
+    if (!t) return;
+    memset(t, 0, sizeof(*t));
+    t->measure_separate = 1;
+    t->measure_total = 1;
+}
+void g4s_timings_add(g4s_timings *a, const g4s_timings *b) {
+    a->create += b->create;
+    a->spmm += b->spmm;
+    a->convert += b->convert;
+    a->order += b->order;
+    a->export_csr += b->export_csr;
+    a->destroy += b->destroy;
+    a->total += b->total;
+}
+void g4s_timings_div(g4s_timings *t, double x) {
+    t->create /= x;
+    t->spmm /= x;
+    t->convert /= x;
+    t->order /= x;
+    t->export_csr /= x;
+    t->destroy /= x;
+    t->total /= x;
+}
+void g4s_timings_print(const g4s_timings *t, double total_flop) {
+    const double g = total_flop / 1e9;
+    const double sum = t->create + t->spmm + t->convert + t->order + t->export_csr + t->destroy;
+    printf("total flop %lf\n", total_flop);
+    if (!t->measure_separate) return;
+    const char *names[6] = {"create", "spmm", "convert", "order", "export_csr", "destroy"};
+    const double v[6] = {t->create, t->spmm, t->convert, t->order, t->export_csr, t->destroy};
+    printf("time(ms):\n");
+    for (int i = 0; i < 6; ++i) printf("    %-18s %8.3lfms %6.2lf%%\n", names[i], 1000 * v[i], v[i] / t->total * 100);
+    printf("    %-18s %8.3lfms %6.2lf%%\n", "sum_total", 1000 * sum, sum / t->total * 100);
+    printf("perf(Gflops):\n");
+    for (int i = 0; i < 6; ++i) printf("    %-18s %6.2lf\n", names[i], g / v[i]);
+    printf("    %-18s %6.2lf\n", "total", g / t->total);
+}
+
+// ---- CSR handles ----------------------------------------------------------------------------------------
+int g4s_csr_create_host(g4s_csr_t *out, int rows, int cols, const int *rowptr, const int *colids,
+                        const double *values) {
+    if (!out || rows < 0 || cols < 0 || !rowptr) return fail(G4S_ERR_INVALID, "g4s_csr_create_host: bad arguments");
+    const long long nnz = rowptr[rows];
+    if (nnz < 0 || (nnz > 0 && (!colids || !values)))
+        return fail(G4S_ERR_INVALID, "g4s_csr_create_host: null colids/values");
+    int rc = ensure_device();
+    if (rc) return rc;
+    g4s_csr *h = nullptr;
+    rc = alloc_csr(&h, rows, cols, nnz);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy(h->rowptr, rowptr, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(h->colids, colids, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(h->values, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        g4s_csr_destroy(h);
+        return fail(G4S_ERR_CUDA, std::string("H2D copy of CSR: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return G4S_OK;
+}
+
+int g4s_csr_create_device(g4s_csr_t *out, int rows, int cols, const int *rowptr_dev, const int *colids_dev,
+                          const double *values_dev, void *stream) {
+    if (!out || rows < 0 || cols < 0 || !rowptr_dev) return fail(G4S_ERR_INVALID, "g4s_csr_create_device: bad arguments");
+    if (!aligned16(rowptr_dev) || !aligned16(colids_dev) || !aligned16(values_dev))
+        return fail(G4S_ERR_INVALID, "g4s_csr_create_device: device arrays must be 16-byte aligned");
+    int rc = ensure_device();
+    if (rc) return rc;
+    int nnz = 0;
+    G4S_CUDA(cudaMemcpyAsync(&nnz, rowptr_dev + rows, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    G4S_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (nnz < 0) return fail(G4S_ERR_INVALID, "g4s_csr_create_device: negative nnz");
+    g4s_csr *h = new (std::nothrow) g4s_csr();
+    if (!h) return fail(G4S_ERR_ALLOC, "host allocation failed");
+    h->rows = rows;
+    h->cols = cols;
+    h->nnz = nnz;
+    h->rowptr = const_cast<int *>(rowptr_dev);
+    h->colids = const_cast<int *>(colids_dev);
+    h->values = const_cast<double *>(values_dev);
+    h->owns = false;
+    *out = h;
+    return G4S_OK;
+}
+
+int g4s_csr_destroy(g4s_csr_t h) {
+    if (!h) return G4S_OK;
+    spmv_free_plan(h);
+    if (h->owns) {
+        if (h->rowptr) cudaFree(h->rowptr);
+        if (h->colids) cudaFree(h->colids);
+        if (h->values) cudaFree(h->values);
+    }
+    if (h->x_dev) cudaFree(h->x_dev);
+    if (h->y_dev) cudaFree(h->y_dev);
+    delete h;
+    return G4S_OK;
+}
+
+int g4s_csr_shape(g4s_csr_t h, int *rows, int *cols, long long *nnz) {
+    if (!h) return fail(G4S_ERR_INVALID, "null handle");
+    if (rows) *rows = h->rows;
+    if (cols) *cols = h->cols;
+    if (nnz) *nnz = h->nnz;
+    return G4S_OK;
+}
+
+int g4s_csr_device_arrays(g4s_csr_t h, const int **rowptr_dev, const int **colids_dev, const double **values_dev) {
+    if (!h) return fail(G4S_ERR_INVALID, "null handle");
+    if (rowptr_dev) *rowptr_dev = h->rowptr;
+    if (colids_dev) *colids_dev = h->colids;
+    if (values_dev) *values_dev = h->values;
+    return G4S_OK;
+}
+
+int g4s_csr_download(g4s_csr_t h, int *rowptr, int *colids, double *values) {
+    if (!h) return fail(G4S_ERR_INVALID, "null handle");
+    if (rowptr) G4S_CUDA(cudaMemcpy(rowptr, h->rowptr, sizeof(int) * ((size_t)h->rows + 1), cudaMemcpyDeviceToHost));
+    if (colids && h->nnz) G4S_CUDA(cudaMemcpy(colids, h->colids, sizeof(int) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    if (values && h->nnz) G4S_CUDA(cudaMemcpy(values, h->values, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+    return G4S_OK;
+}
+
+// ---- SpMV -----------------------------------------------------------------------------------------------
+int g4s_spmv_device(g4s_csr_t A, const double *x_dev, double *y_dev, void *stream) {
+    if (!A || (!x_dev && A->cols) || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_device: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return spmv_run(A, x_dev, y_dev, nullptr, false, (cudaStream_t)stream);
+}
+
+int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const int *row_map_dev, int accumulate,
+                       void *stream) {
+    if (!A || (!x_dev && A->cols) || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_device_ex: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return spmv_run(A, x_dev, y_dev, row_map_dev, accumulate != 0, (cudaStream_t)stream);
+}
+
+int g4s_spmv_host(g4s_csr_t A, const double *x, double *y) {
+    if (!A || (!x && A->cols) || (!y && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_host: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!A->x_dev) G4S_CUDA(cudaMalloc(&A->x_dev, sizeof(double) * (size_t)std::max(A->cols, 1)));
+    if (!A->y_dev) G4S_CUDA(cudaMalloc(&A->y_dev, sizeof(double) * (size_t)std::max(A->rows, 1)));
+    G4S_CUDA(cudaMemcpyAsync(A->x_dev, x, sizeof(double) * (size_t)A->cols, cudaMemcpyHostToDevice, 0));
+    rc = spmv_run(A, A->x_dev, A->y_dev, nullptr, false, 0);
+    if (rc) return rc;
+    G4S_CUDA(cudaMemcpyAsync(y, A->y_dev, sizeof(double) * (size_t)A->rows, cudaMemcpyDeviceToHost, 0));
+    G4S_CUDA(cudaStreamSynchronize(0));
+    return G4S_OK;
+}
+
+int g4s_spmv_csr_f64(int rows, int cols, const int *rowptr, const int *colids, const double *values,
+                     const double *x, double *y) {
+    g4s_csr_t h = nullptr;
+    int rc = g4s_csr_create_host(&h, rows, cols, rowptr, colids, values);
+    if (rc) return rc;
+    rc = g4s_spmv_host(h, x, y);
+    g4s_csr_destroy(h);
+    return rc;
+}
+
+int g4s_spmv_cost(g4s_csr_t A, double *bytes, double *flops) {
+    if (!A) return fail(G4S_ERR_INVALID, "null handle");
+    if (bytes) *bytes = 12.0 * (double)A->nnz + 4.0 * ((double)A->rows + 1) + 8.0 * (double)A->cols + 8.0 * (double)A->rows;
+    if (flops) *flops = 2.0 * (double)A->nnz;
+    return G4S_OK;
+}
+
+int g4s_spmv_set_tuning(g4s_csr_t A, int lanes_per_row, int variant) {
+    if (!A) return fail(G4S_ERR_INVALID, "null handle");
+    if (lanes_per_row < 0 || lanes_per_row > 32 || (lanes_per_row & (lanes_per_row - 1)))
+        return fail(G4S_ERR_INVALID, "lanes_per_row must be 0 or a power of two <= 32");
+    A->plan.lanes_per_row = lanes_per_row;
+    A->plan.variant = variant;
+    return G4S_OK;
+}
+
+int g4s_partition_rows_i32(const int *work_prefix, int rows, int parts, int *cuts) {
+    return partition_rows(work_prefix, rows, parts, cuts);
+}
+int g4s_partition_rows_i64(const long long *work_prefix, int rows, int parts, int *cuts) {
+    return partition_rows(work_prefix, rows, parts, cuts);
+}
+
+void g4s_free(void *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Shared device/host helpers for the g4s_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/g4s_b200.h"
+
+namespace g4s {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int status, const std::string &msg);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define G4S_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::g4s::fail(G4S_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+#define G4S_CHECK_LAUNCH(name)                                                                           \
+    do {                                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                                             \
+        if (_e != cudaSuccess)                                                                           \
+            return ::g4s::fail(G4S_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+        ::g4s::count_launch();                                                                           \
+    } while (0)
+
+int ensure_device();  // G4S_OK when the current device is usable (sm_100), else G4S_ERR_CUDA
+int sm_count();
+
+// ---- the CSR handle ---------------------------------------------------------------------------------
+struct SpmvPlan {
+    int tile_items = 0;        // merge items (rows + nnz) per tile
+    int ntiles = 0;
+    int *tile_row = nullptr;   // [ntiles+1] first row of each tile (merge-path coordinate)
+    double *carry = nullptr;   // [ntiles]   partial sum of the row left open at the end of each tile
+    int lanes_per_row = 0;     // 0 = automatic
+    int variant = 0;           // 0 = automatic
+    int max_row_len = 0;
+};
+
+}  // namespace g4s
+
+struct g4s_csr {
+    int rows = 0, cols = 0;
+    long long nnz = 0;
+    int *rowptr = nullptr;
+    int *colids = nullptr;
+    double *values = nullptr;
+    bool owns = false;
+    g4s::SpmvPlan plan;
+    // scratch for the host-pointer entry points
+    double *x_dev = nullptr, *y_dev = nullptr;
+};
+
+namespace g4s {
+
+// ---- PTX wrappers: mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// L2 eviction policy for data that is streamed exactly once (matrix arrays): keep x / y resident instead.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16, completes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ double ldg_f64(const double *p) { return __ldg(p); }
+
+}  // namespace g4s

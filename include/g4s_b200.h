@@ -1,0 +1,197 @@
+/* g4s_b200 — C ABI of the B200-native mv/ (matrix-vector) and mm/ (matrix-matrix) hot path of G4S.
+ *
+ * Plain C: pointers, sizes and opaque handles only; no C++ or torch types cross this boundary.
+ * Every entry names the reference interface it replaces (paths relative to the reference tree).
+ * All functions return G4S_OK (0) or a negative g4s_status and never throw or abort; the text of the last
+ * error on the calling thread is available from g4s_last_error().  There is NO CPU fallback: every compute
+ * entry fails with G4S_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Conventions kept from the reference (mm/inc/CSR.h:22-100): CSR<int,double>, 0-based, rowptr[rows+1],
+ * colids[nnz], values[nnz]; SpGEMM output has column ids sorted ascending inside each row (the reference's
+ * mkl_sparse_order, mm/inc/mkl_mult.h:70, and HashSpGEMM<sortOutput=true>, mm/inc/hash_mult.h:525-553).
+ *
+ * Pointer spaces: `_host` entries take host memory and do their own H2D/D2H copies; `_device` entries take
+ * device memory on the current CUDA device (16-byte aligned bases) and a cudaStream_t passed as void*.
+ */
+#ifndef G4S_B200_H
+#define G4S_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum g4s_status {
+    G4S_OK = 0,
+    G4S_ERR_INVALID = -1, /* bad argument (null pointer, negative size, misaligned device pointer) */
+    G4S_ERR_CUDA = -2,    /* CUDA runtime error or no usable device */
+    G4S_ERR_ALLOC = -3,   /* host or device allocation failed */
+    G4S_ERR_IO = -4,      /* file missing or unreadable */
+    G4S_ERR_FORMAT = -5,  /* malformed MatrixMarket / edge-list input (the reference throws std::runtime_error) */
+    G4S_ERR_SHAPE = -6    /* non-conformable operands */
+} g4s_status;
+
+const char *g4s_last_error(void);
+const char *g4s_version(void);
+/* Number of kernels this library has launched on behalf of the calling process (bench.py's gpu_launches). */
+long long g4s_kernel_launch_count(void);
+int g4s_device_count(void);
+int g4s_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Timings — C twin of class Timings (mm/inc/Timings.h:4-22): two bools then seven doubles, seconds.
+ * Layout-compatible with the reference class (standard layout, no virtuals), so a `Timings&` can be passed
+ * as `g4s_timings*` from C++.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct g4s_timings {
+    unsigned char measure_separate;
+    unsigned char measure_total;
+    double create;     /* upload / handle creation            (mkl_sparse_d_create_csr, mkl_mult.h:50-53) */
+    double spmm;       /* symbolic + numeric product           (mkl_sparse_spmm,        mkl_mult.h:58)    */
+    double convert;    /* always 0: output is CSR already      (mkl_sparse_convert_csr, mkl_mult.h:64)    */
+    double order;      /* in-kernel column sort, counted in spmm; 0 here (mkl_sparse_order, mkl_mult.h:70) */
+    double export_csr; /* D2H of crpt/ccol/cval                (mkl_sparse_d_export_csr, mkl_mult.h:79)   */
+    double destroy;    /* device frees                          (mkl_sparse_destroy,     mkl_mult.h:102-106) */
+    double total;
+} g4s_timings;
+void g4s_timings_init(g4s_timings *t);                           /* Timings::Timings,  mm/src/Timings.cpp:4-14  */
+void g4s_timings_add(g4s_timings *acc, const g4s_timings *t);    /* operator+=,        Timings.cpp:16-24        */
+void g4s_timings_div(g4s_timings *t, double x);                  /* operator/=,        Timings.cpp:26-34        */
+void g4s_timings_print(const g4s_timings *t, double total_flop); /* Timings::print,    Timings.cpp:36-60        */
+
+/* ------------------------------------------------------------------------------------------------------
+ * CSR handle — device-resident CSR<int,double> plus the SpMV inspector data (merge-path tile table).
+ * Plays the role of MKL's sparse_matrix_t in the reference (mkl_sparse_d_create_csr / mkl_sparse_destroy,
+ * mm/inc/mkl_mult.h:50-53,102-106).  NEW API SURFACE: the reference has no sparse mat-vec (mv/mv.c is dense).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct g4s_csr *g4s_csr_t;
+
+/* copies host arrays to the device (owned by the handle) */
+int g4s_csr_create_host(g4s_csr_t *out, int rows, int cols, const int *rowptr, const int *colids,
+                        const double *values);
+/* borrows device arrays (caller keeps them alive); nnz = rowptr[rows] is read back once */
+int g4s_csr_create_device(g4s_csr_t *out, int rows, int cols, const int *rowptr_dev, const int *colids_dev,
+                          const double *values_dev, void *stream);
+int g4s_csr_destroy(g4s_csr_t h);
+int g4s_csr_shape(g4s_csr_t h, int *rows, int *cols, long long *nnz);
+/* device pointers of the handle's arrays (for callers that want to run their own kernels / collectives) */
+int g4s_csr_device_arrays(g4s_csr_t h, const int **rowptr_dev, const int **colids_dev, const double **values_dev);
+/* copy the handle's arrays back to host buffers sized rows+1 / nnz / nnz */
+int g4s_csr_download(g4s_csr_t h, int *rowptr, int *colids, double *values);
+
+/* y = A x  (alpha = 1, beta = 0 — the only combination mv/mv.c:6-27 uses).
+ * Replaces, for sparse A, matrix_multiply_dgemv (mv/mv.c:23-27). */
+int g4s_spmv_device(g4s_csr_t A, const double *x_dev, double *y_dev, void *stream);
+int g4s_spmv_host(g4s_csr_t A, const double *x, double *y); /* H2D x, kernel, D2H y, synchronous */
+/* one-shot: create + spmv + destroy, all arrays on the host */
+int g4s_spmv_csr_f64(int rows, int cols, const int *rowptr, const int *colids, const double *values,
+                     const double *x, double *y);
+/* Algorithmic bytes and flops of one SpMV: 12 nnz + 4(rows+1) + 8 cols + 8 rows; 2 nnz. */
+int g4s_spmv_cost(g4s_csr_t A, double *bytes, double *flops);
+/* Tuning knobs (0 = automatic): lanes cooperating on one row (1..32, power of two), kernel variant. */
+int g4s_spmv_set_tuning(g4s_csr_t A, int lanes_per_row, int variant);
+
+/* Extended form used by the multi-GPU path, where each GPU holds its row block split into a diagonal block
+ * (columns it owns) and a row-compressed off-diagonal block: local row r of A is written to y[row_map[r]]
+ * (row_map_dev NULL = identity) and accumulate != 0 turns the store into y += A x. */
+int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const int *row_map_dev, int accumulate,
+                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense mv entry points, same names and signatures as the reference (mv/mv.c:6-27); host buffers,
+ * `dim x dim` doubles.  A is interpreted exactly as the reference's CBLAS calls do (column-major view of
+ * the row-major-filled buffer, upper triangle):
+ *   dgemv : C = A_cm B            dsymv : C = sym(upper(A_cm)) B
+ *   dtrmv : B <- upper(A_cm)^T B  (C untouched)      sspmv : C = sympacked(A) B  (cblas_dspmv on A as packed)
+ * They upload A, run one HBM-bound kernel and download the result; failures are reported on stderr
+ * (the reference signatures return void) and leave outputs untouched.
+ * ---------------------------------------------------------------------------------------------------- */
+void matrix_multiply_dgemv(double *A, double *B, double *C, int dim);
+void matrix_multiply_dsymv(double *A, double *B, double *C, int dim);
+void matrix_multiply_dtrmv(double *A, double *B, double *C, int dim);
+void matrix_multiply_sspmv(double *A, double *B, double *C, int dim);
+/* status-returning twins on device memory */
+int g4s_dense_mv_device(int op /*0 dgemv,1 dsymv,2 dtrmv,3 dspmv*/, const double *A_dev, double *B_dev,
+                        double *C_dev, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * SpGEMM  C = A B, CSR x CSR -> CSR, sorted columns.
+ * ---------------------------------------------------------------------------------------------------- */
+/* Allocator the caller's free routine matches (the reference frees mkl()'s outputs with my_free,
+ * mm/inc/CSR.h:50-62 / utility.h:141-153).  NULL selects malloc (release with g4s_free). */
+typedef void *(*g4s_alloc_fn)(size_t bytes, void *ctx);
+
+/* C twin of  void mkl(int*arpt,int*acol,double*aval,int*brpt,int*bcol,double*bval,
+ *                     int**crpt_,int**ccol_,double**cval_,int M,int K,int N,int*cnnz_,Timings&timing)
+ * (mm/inc/mkl_mult.h:40-110): host CSR in, callee-allocated host CSR out, crpt has M+1 entries with
+ * crpt[M] = cnnz, phases reported in `timing` (may be NULL). */
+int g4s_mkl(const int *arpt, const int *acol, const double *aval, const int *brpt, const int *bcol,
+            const double *bval, int **crpt_, int **ccol_, double **cval_, int M, int K, int N, int *cnnz_,
+            g4s_timings *timing);
+int g4s_mkl_alloc(const int *arpt, const int *acol, const double *aval, const int *brpt, const int *bcol,
+                  const double *bval, int **crpt_, int **ccol_, double **cval_, int M, int K, int N, int *cnnz_,
+                  g4s_timings *timing, g4s_alloc_fn alloc_index, g4s_alloc_fn alloc_value, void *alloc_ctx);
+void g4s_free(void *p);
+
+/* Device-resident SpGEMM on handles (HashSpGEMM(a,b,c,...), mm/inc/hash_mult.h:1028-1057): returns a new
+ * handle that owns C.  Symbolic and numeric phases run on `stream`; the call synchronises once, after the
+ * symbolic phase, to size C. */
+int g4s_spgemm_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
+/* Per-phase device milliseconds of the last g4s_spgemm_device on this thread: binning, symbolic, scan+alloc,
+ * numeric(+sort). */
+int g4s_spgemm_last_phase_ms(double *ms4);
+
+/* compute_flop / get_flop (mm/inc/mkl_mult.h:8-38, hash_mult.h:45-62): intermediate products, 64-bit.
+ * row_work_dev may be NULL; else int32[rows] on the device (BIN::set_intprod_num, BIN.h:77-95). */
+int g4s_compute_flop_device(g4s_csr_t A, g4s_csr_t B, long long *total, int *row_work_dev, void *stream);
+long long compute_flop_host(const int *arpt, const int *acol, const int *brpt, int M); /* host twin */
+
+/* ------------------------------------------------------------------------------------------------------
+ * Partitioner — BIN::set_rows_offset (mm/inc/BIN.h:100-122) generalised from threads to GPUs: contiguous
+ * row ranges of (nearly) equal work.  work_prefix = exclusive prefix sum with rows+1 entries (rowptr itself
+ * for an nnz balance).  Cut p = lower_bound(prefix, ceil(total/parts)*(p+1)), last cut = rows; 64-bit
+ * arithmetic, cuts clamped to `rows` (the reference's int arithmetic overflows, and its cuts can pass the
+ * last row for tiny inputs).
+ * ---------------------------------------------------------------------------------------------------- */
+int g4s_partition_rows_i32(const int *work_prefix, int rows, int parts, int *cuts /* parts+1 */);
+int g4s_partition_rows_i64(const long long *work_prefix, int rows, int parts, int *cuts);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Loaders (host) — CSR::construct (mm/inc/CSR.h:485-669) and CSR(graph&) (mm/inc/CSR.h:255-329).
+ * Outputs are malloc'd (g4s_free).
+ * ---------------------------------------------------------------------------------------------------- */
+int g4s_csr_read_matrix_market(const char *path, int *rows, int *cols, int *nnz, int **rowptr, int **colids,
+                               double **values);
+/* edge list laid out as class graph (mm/inc/graph.h:4-25): long start[m], end[m]; double w[m]; n vertices */
+int g4s_csr_from_edge_list(long m, long n, const long *start, const long *end, const double *w, int *nnz,
+                           int **rowptr, int **colids, double **values);
+/* CSR(const CSR&, M_, N_, M_start, N_start) (mm/inc/CSR.h:691-733) */
+int g4s_csr_submatrix(int rows, int cols, const int *rowptr, const int *colids, const double *values, int M_,
+                      int N_, int M_start, int N_start, int *nnz, int **orpt, int **ocol, double **oval);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Synthetic inputs of BASELINE.json's configs, generated directly in CSR on the device.
+ * Natural ordering, row = (k*n + j)*n + i.   2-D 5-point: diag 4, off-diag -1.  3-D 27-point: diag 26,
+ * off-diag -1.  Rows [row0, row1) only (row-partitioned generation for multi-GPU); column ids stay global.
+ * ---------------------------------------------------------------------------------------------------- */
+long long g4s_laplacian2d_nnz(int n, long long row0, long long row1);
+long long g4s_laplacian3d27_nnz(int n, long long row0, long long row1);
+int g4s_csr_generate_laplacian2d(g4s_csr_t *out, int n, long long row0, long long row1, void *stream);
+int g4s_csr_generate_laplacian3d27(g4s_csr_t *out, int n, long long row0, long long row1, void *stream);
+/* Graph500 R-MAT (a,b,c,d = .57,.19,.19,.05), 2^scale vertices, edge_factor * 2^scale generated edges,
+ * weights U(0,1), duplicates summed (CSR(graph&) semantics); counter-based generator keyed by `seed`. */
+int g4s_csr_generate_rmat(g4s_csr_t *out, int scale, int edge_factor, unsigned long long seed, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * BSR SpMM (BASELINE config 5): C[mb*bs, ncol] = A_bsr B, bs x bs row-major blocks, row-major dense B, C.
+ * No counterpart in the reference; FP64 tensor-core (DMMA) path for bs = 3.
+ * ---------------------------------------------------------------------------------------------------- */
+int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const int *bcolids_dev,
+                        const double *bvalues_dev, int ncol, const double *B_dev, double *C_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4S_B200_H */

@@ -46,13 +46,15 @@ def powerlaw_csr(rows, seed, max_deg=None):
     """Rows with Zipf-distributed lengths (a few very long rows, many empty ones): merge-path territory."""
     rng = np.random.default_rng(seed)
     deg = np.minimum(rng.zipf(1.6, rows) - 1, max_deg or rows)
-    deg[rng.integers(0, rows)] = min(rows, 20000)  # one hub row
+    deg[rng.integers(0, rows)] = min(rows, max_deg or 20000)  # one hub row
+    r = np.repeat(np.arange(rows, dtype=np.int64), deg)
+    c = rng.integers(0, rows, len(r))
+    key = np.unique(r * rows + c)  # sorted (row, col), duplicates dropped
+    r, c = key // rows, key % rows
     rowptr = np.zeros(rows + 1, dtype=np.int64)
-    np.cumsum(deg, out=rowptr[1:])
-    cols = np.concatenate([np.sort(rng.choice(rows, size=d, replace=False)) for d in deg if d > 0]) \
-        if rowptr[-1] else np.zeros(0, dtype=np.int64)
-    vals = rng.uniform(-1.0, 1.0, int(rowptr[-1]))
-    return (rows, rows, rowptr.astype(np.int32), cols.astype(np.int32), vals)
+    np.cumsum(np.bincount(r, minlength=rows), out=rowptr[1:])
+    vals = rng.uniform(-1.0, 1.0, len(c))
+    return (rows, rows, rowptr.astype(np.int32), c.astype(np.int32), vals)
 
 
 def tridiag3():
