@@ -37,13 +37,16 @@ int sm_count();
 
 // ---- the CSR handle ---------------------------------------------------------------------------------
 struct SpmvPlan {
-    int tile_items = 0;        // merge items (rows + nnz) per tile
-    int ntiles = 0;
-    int *tile_row = nullptr;   // [ntiles+1] first row of each tile (merge-path coordinate)
-    double *carry = nullptr;   // [ntiles]   partial sum of the row left open at the end of each tile
-    int lanes_per_row = 0;     // 0 = automatic
-    int variant = 0;           // 0 = automatic
+    int cap = 0;                        // max nonzeros per chunk
+    int nchunks = 0;
+    int2 *desc = nullptr;               // [nchunks+1] (first row, first nnz) of each chunk
+    unsigned char *lanes_lg = nullptr;  // [nchunks]   log2(lanes per row) chosen by the inspector
+    double *carry = nullptr;            // [nchunks]   partial sums of non-final pieces of long rows
+    int4 *long_rows = nullptr;          // [n_long]    (row, first chunk, pieces, -)
+    int n_long = 0;                     // rows longer than cap
     int max_row_len = 0;
+    int lanes_per_row = 0;              // tuning override, 0 = inspector's choice
+    int variant = 0;                    // tuning override, 0 = default kernel shape
 };
 
 }  // namespace g4s

@@ -4,19 +4,19 @@
 // the reference's own CSR container (mm/inc/CSR.h:22-100).
 //
 // Design:
-//  * Inspector (once per matrix, like mkl_sparse_optimize): the merge list "row ends ∪ nnz indices" is cut
-//    into tiles of TILE items; tile t starts at row tile_row[t] and nnz t*TILE - tile_row[t] (merge-path
-//    diagonal search).  Every tile therefore owns at most TILE rows AND at most TILE nonzeros, whatever the
-//    row-length distribution (power-law rows, millions of empty rows).
-//  * Executor: persistent CTAs; each walks tiles blockIdx.x, +gridDim.x, ...  A tile's colids / values /
-//    rowptr slices are contiguous in HBM and are brought into shared memory by the TMA engine as 1-D bulk
-//    async copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict_first) through a STAGES-deep ring, so
-//    the HBM stream never waits for arithmetic.  x is gathered with ld.global.nc and lives in L1/L2.
-//  * Inside a tile, L = 2^k lanes cooperate on a row (L from the tile's mean row length), reading the
-//    staged arrays from shared memory (conflict-free for odd row lengths) and reducing with shuffles;
-//    rows far longer than the mean are swept by the whole CTA.
-//  * A row cut by a tile boundary leaves its partial sum in carry[t]; a tiny fix-up kernel adds the carries
-//    in tile order (deterministic: no atomics anywhere).
+//  * Inspector (once per matrix, like mkl_sparse_optimize): rows are grouped into CHUNKS of at most 32 rows
+//    and at most CAP nonzeros; a row longer than CAP is cut into CAP-sized pieces, one chunk each.  A chunk
+//    is the pair (first row, first nnz); chunk c ends where chunk c+1 starts.  For every chunk the inspector
+//    also picks L = 2^k lanes per row from the chunk's own row lengths (cost model below), so short regular
+//    rows run lane-per-row and skewed (power-law) chunks spread a long row over many lanes.
+//  * Executor: persistent CTAs of autonomous warps.  A warp owns a chunk at a time: lane 0 asks the TMA
+//    engine for the chunk's colids/values slices (two 1-D bulk async copies, cp.async.bulk + mbarrier
+//    complete_tx, L2 evict_first) into the warp's private shared-memory ring, the warp waits on its own
+//    mbarrier, multiplies out of shared memory (bank-conflict-free for odd row lengths), and stores y
+//    coalesced.  No CTA-wide barrier exists; NBUF chunks per warp are in flight so HBM never waits for
+//    arithmetic.  x is gathered with ld.global.nc and is served by L1/L2.
+//  * Pieces of a long row leave partial sums in carry[chunk]; one thread per long row adds them in order
+//    (deterministic; no atomics anywhere).
 #include <algorithm>
 #include <vector>
 
@@ -24,165 +24,318 @@
 
 namespace g4s {
 
+constexpr int CHUNK_ROWS = 32;
+
 // ------------------------------------------------------------------------------------------------------
-// Inspector: merge-path diagonal search, one thread per tile boundary.
-// Item d of the merge is "row end i" if rowptr[i+1] <= d - i - 1 ... (CUB-style coordinate search).
+// small device-wide exclusive scan (int32), three launches; also used by SpGEMM for C's row pointers
 // ------------------------------------------------------------------------------------------------------
-__global__ void spmv_tile_search_kernel(const int *__restrict__ rowptr, int rows, long long nnz, int tile_items,
-                                        int ntiles, int *__restrict__ tile_row) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > ntiles) return;
-    long long total = (long long)rows + nnz;
-    long long d = (long long)t * tile_items;
-    if (d > total) d = total;
-    long long lo = d > nnz ? d - nnz : 0;
-    long long hi = d < rows ? d : rows;
-    while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        // row `mid` ends before nnz index (d - mid - 1) is consumed?
-        if ((long long)__ldg(rowptr + mid + 1) <= d - mid - 1) lo = mid + 1;
-        else hi = mid;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;  // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *warp_sums) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    tile_row[t] = (int)lo;
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    const int base = w ? warp_sums[w - 1] : 0;
+    if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+    return base + incl - v;
 }
 
-__global__ void max_row_len_kernel(const int *__restrict__ rowptr, int rows, int *__restrict__ out) {
-    int m = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x)
-        m = max(m, __ldg(rowptr + i + 1) - __ldg(rowptr + i));
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+__global__ void scan_tile_sums_kernel(const int *__restrict__ in, long long n, long long *__restrict__ tile_sums) {
+    __shared__ int ws[SCAN_THREADS / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        long long k = base + (long long)i * SCAN_THREADS + threadIdx.x;
+        if (k < n) s += in[k];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += ws[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+// single block: exclusive scan of tile sums in place, grand total to tile_sums[ntiles]
+__global__ void scan_tile_offsets_kernel(long long *tile_sums, int ntiles) {
+    __shared__ long long carry;
+    __shared__ long long wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        long long v = i < ntiles ? tile_sums[i] : 0;
+        long long incl = v;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            long long s = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += t;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const long long off = carry + (w ? wsum[w - 1] : 0) + incl - v;
+        if (i < ntiles) tile_sums[i] = off;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = off + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+// out[k] = exclusive prefix of in (int32 result; caller guarantees the total fits), out may alias in.
+// writes n+1 entries when write_total.
+__global__ void scan_apply_kernel(const int *__restrict__ in, int *__restrict__ out, long long n,
+                                  const long long *__restrict__ tile_offsets, int write_total) {
+    __shared__ int ws[SCAN_THREADS / 32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    int off = block_exclusive_scan(s, nullptr, ws) + (int)tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = off;
+        off += v[i];
+    }
+    if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+        out[n] = (int)tile_offsets[gridDim.x];
+}
+
+// exclusive scan of n int32 counts; total (64-bit) returned through *total_host when non-null (synchronises).
+int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, long long *total_host,
+                       cudaStream_t stream) {
+    const int ntiles = (int)std::max<long long>(1, (n + SCAN_TILE - 1) / SCAN_TILE);
+    long long *tile_sums = nullptr;
+    G4S_CUDA(cudaMallocAsync(&tile_sums, sizeof(long long) * ((size_t)ntiles + 1), stream));
+    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, stream>>>(in, n, tile_sums);
+    G4S_CHECK_LAUNCH("scan_tile_sums_kernel");
+    scan_tile_offsets_kernel<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
+    G4S_CHECK_LAUNCH("scan_tile_offsets_kernel");
+    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, stream>>>(in, out, n, tile_sums, write_total);
+    G4S_CHECK_LAUNCH("scan_apply_kernel");
+    if (total_host) {
+        G4S_CUDA(cudaMemcpyAsync(total_host, tile_sums + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        G4S_CUDA(cudaStreamSynchronize(stream));
+    }
+    G4S_CUDA(cudaFreeAsync(tile_sums, stream));
+    return G4S_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Inspector.  One thread walks one block of 32 consecutive rows and cuts it greedily:
+//   - rows are appended to the open chunk while its nonzeros stay <= cap;
+//   - a row longer than cap closes the open chunk and becomes ceil(len/cap) single-piece chunks.
+// Pass 1 counts chunks per block, a scan turns counts into offsets, pass 2 writes the descriptors.
+// ------------------------------------------------------------------------------------------------------
+struct ChunkWalk {
+    int cap;
+    // cost model (in "inner-loop iterations") for running a chunk with L = 1<<lg lanes per row
+    __device__ static int lanes_for(const int *len, int nrows) {
+        int best = 0, best_cost = 0x7fffffff;
+        for (int lg = 0; lg <= 5; ++lg) {
+            const int L = 1 << lg, per_pass = 32 >> lg;
+            int cost = 0;
+            for (int b = 0; b < nrows; b += per_pass) {
+                int m = 0;
+                for (int r = b; r < min(b + per_pass, nrows); ++r) m = max(m, len[r]);
+                cost += (m + L - 1) / L + 2 + lg;  // iterations + per-pass overhead (bounds, shuffles, store)
+            }
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = lg;
+            }
+        }
+        return best;
+    }
+};
+
+template <bool FILL>
+__global__ void chunk_walk_kernel(const int *__restrict__ rowptr, int rows, int cap, int nblocks,
+                                  int *__restrict__ counts,            // !FILL: out, FILL: exclusive offsets in
+                                  int2 *__restrict__ desc, unsigned char *__restrict__ lanes_lg,
+                                  int4 *__restrict__ long_rows, int *__restrict__ n_long) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const int r_begin = b * CHUNK_ROWS, r_end = min(r_begin + CHUNK_ROWS, rows);
+    int out = FILL ? counts[b] : 0;
+    int n = 0;
+    int len[CHUNK_ROWS];
+    int open_rows = 0, open_nnz = 0, open_row0 = r_begin;
+    int prev = __ldg(rowptr + r_begin);
+    auto close_open = [&]() {
+        if (FILL) {
+            desc[out] = make_int2(open_row0, __ldg(rowptr + open_row0));
+            lanes_lg[out] = (unsigned char)ChunkWalk::lanes_for(len, open_rows);
+        }
+        ++out;
+        ++n;
+        open_rows = 0;
+        open_nnz = 0;
+    };
+    for (int r = r_begin; r < r_end; ++r) {
+        const int next = __ldg(rowptr + r + 1);
+        const int l = next - prev;
+        if (l > cap) {
+            if (open_rows) close_open();
+            const int pieces = (l + cap - 1) / cap;
+            if (FILL) {
+                for (int p = 0; p < pieces; ++p) {
+                    desc[out + p] = make_int2(r, prev + p * cap);
+                    lanes_lg[out + p] = 5;
+                }
+                long_rows[atomicAdd(n_long, 1)] = make_int4(r, out, pieces, 0);
+            }
+            out += pieces;
+            n += pieces;
+            open_row0 = r + 1;
+        } else {
+            if (open_nnz + l > cap) close_open();
+            if (open_rows == 0) open_row0 = r;
+            len[open_rows++] = l;
+            open_nnz += l;
+        }
+        prev = next;
+    }
+    if (open_rows) close_open();
+    if (!FILL) counts[b] = n;
+}
+
+__global__ void count_long_rows_kernel(const int *__restrict__ rowptr, int rows, int cap, int *__restrict__ n_long,
+                                       int *__restrict__ max_len) {
+    int c = 0, m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int l = __ldg(rowptr + i + 1) - __ldg(rowptr + i);
+        c += l > cap;
+        m = max(m, l);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c) atomicAdd(n_long, c);
+        if (m) atomicMax(max_len, m);
+    }
+}
+
+__global__ void write_sentinel_kernel(int2 *desc, int nchunks, int rows, const int *rowptr) {
+    desc[nchunks] = make_int2(rows, rowptr[rows]);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Executor
 // ------------------------------------------------------------------------------------------------------
-template <int TILE>
-struct alignas(32) SpmvStage {
-    double vals[TILE + 8];
-    int cols[TILE + 8];
-    int rp[TILE + 16];
-    int desc[8];  // row0, row1, nnz0, nnz1
-};
-
 struct SpmvArgs {
     const int *rowptr;
     const int *colids;
     const double *values;
     const double *x;
     double *y;
-    const int *tile_row;
+    const int2 *desc;
+    const unsigned char *lanes_lg;
     double *carry;
     const int *row_map;  // optional: local row r is y[row_map[r]] (row-compressed off-diagonal blocks)
     int rows;
     long long nnz;
-    int ntiles;
-    int lanes_log2;  // -1: per-tile automatic
+    int nchunks;
+    int force_lg;  // -1: use the inspector's choice
 };
 
-template <int L, int THREADS>
-__device__ __forceinline__ double group_reduce(double v) {
-#pragma unroll
-    for (int o = L >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+template <int CAP>
+struct alignas(32) ChunkBuf {
+    double vals[CAP + 8];
+    int cols[CAP + 8];
+};
 
-// ACCUM: y[row] += sum instead of y[row] = sum (second pass of the split multi-GPU product).
-template <int TILE, int THREADS, int L, bool ACCUM>
-__device__ __forceinline__ void tile_rows(const SpmvStage<TILE> &st, const SpmvArgs &a, int tile, int *long_rows,
-                                          int *n_long, double *red) {
-    const int row0 = st.desc[0], row1 = st.desc[1], nnz0 = st.desc[2], nnz1 = st.desc[3];
+template <int L, int CAP, bool ACCUM>
+__device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvArgs &a, int chunk, int row0,
+                                           int row1, int nnz0, int nnz1, int lane, int rp0, int rp1) {
     const int a0 = nnz0 & ~3;
-    const int rbase = row0 - (row0 & ~3);
     const int R = row1 - row0;
-    const int nloc = R + (row1 < a.rows ? 1 : 0);  // rows ending here + the row left open at the end
-    constexpr int GROUPS = THREADS / L;
-    const int gid = threadIdx.x / L, lane = threadIdx.x % L;
-    constexpr int LONG = 64 * L;
+    const int nloc = R > 0 ? R : 1;  // R == 0: a non-final piece of a long row (its sum goes to carry)
+    constexpr int PER_PASS = 32 / L;
+    const int g = lane / L, sub = lane % L;
     const double *__restrict__ x = a.x;
-
-    for (int base = 0; base < nloc; base += GROUPS) {
-        const int r = base + gid;
+    for (int base = 0; base < nloc; base += PER_PASS) {
+        const int r = base + g;
         int s = 0, e = 0;
         if (r < nloc) {
-            s = max(st.rp[rbase + r], nnz0);
-            e = min(st.rp[rbase + r + 1], nnz1);
-        }
-        bool is_long = (e - s) > LONG;
-        if (is_long) {
-            if (lane == 0) long_rows[atomicAdd(n_long, 1)] = r;
-            e = s;
+            if (base) {  // the first pass's row pointers were loaded before the wait on the copy
+                rp0 = __ldg(a.rowptr + row0 + r);
+                rp1 = __ldg(a.rowptr + row0 + r + 1);
+            }
+            s = max(rp0, nnz0);
+            e = min(rp1, nnz1);
         }
         double acc = 0.0;
-        int k = s + lane - a0;
+        int k = s + sub - a0;
         const int ke = e - a0;
 #pragma unroll 4
-        for (; k < ke; k += L) acc = fma(st.vals[k], __ldg(x + st.cols[k]), acc);
-        if (L > 1) acc = group_reduce<L, THREADS>(acc);
-        if (lane == 0 && r < nloc && !is_long) {
-            if (r < R) {
-                const int row = a.row_map ? a.row_map[row0 + r] : row0 + r;
+        for (; k < ke; k += L) acc = fma(buf.vals[k], __ldg(x + buf.cols[k]), acc);
+#pragma unroll
+        for (int o = L >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && r < nloc) {
+            if (R > 0) {
+                const int row = a.row_map ? __ldg(a.row_map + row0 + r) : row0 + r;
                 if (ACCUM) a.y[row] += acc;
                 else a.y[row] = acc;
             } else {
-                a.carry[tile] = acc;
+                a.carry[chunk] = acc;
             }
         }
-    }
-    // rows far above the tile's mean length: the whole CTA sweeps each one
-    __syncthreads();
-    const int nl = *n_long;
-    for (int i = 0; i < nl; ++i) {
-        const int r = long_rows[i];
-        const int s = max(st.rp[rbase + r], nnz0) - a0, e = min(st.rp[rbase + r + 1], nnz1) - a0;
-        double acc = 0.0;
-        for (int k = s + threadIdx.x; k < e; k += THREADS) acc = fma(st.vals[k], __ldg(x + st.cols[k]), acc);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < THREADS / 32; ++w) t += red[w];
-            if (r < R) {
-                const int row = a.row_map ? a.row_map[row0 + r] : row0 + r;
-                if (ACCUM) a.y[row] += t;
-                else a.y[row] = t;
-            } else {
-                a.carry[tile] = t;
-            }
-        }
-        __syncthreads();
     }
 }
 
-template <int TILE, int STAGES, int THREADS, bool ACCUM>
-__global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const SpmvArgs a) {
+template <int CAP, int NBUF, int WARPS, bool ACCUM>
+__global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SpmvStage<TILE> *stages = reinterpret_cast<SpmvStage<TILE> *>(smem_raw);
-    __shared__ uint64_t full[STAGES];
-    __shared__ int long_rows[TILE / 64 + 64];
-    __shared__ int n_long;
-    __shared__ double red[THREADS / 32];
-
-    const int tid = threadIdx.x;
-    const long long total_items = (long long)a.rows + a.nnz;
+    __shared__ uint64_t bars[WARPS * NBUF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ChunkBuf<CAP> *bufs = reinterpret_cast<ChunkBuf<CAP> *>(smem_raw) + warp * NBUF;
+    uint64_t *bar = bars + warp * NBUF;
     uint64_t policy = 0;
 
-    // producer (thread 0): stage one tile
-    auto issue = [&](int stage, int tile) {
-        SpmvStage<TILE> &st = stages[stage];
-        const int row0 = __ldg(a.tile_row + tile), row1 = __ldg(a.tile_row + tile + 1);
-        const long long d0 = (long long)tile * TILE;
-        const long long d1 = min(d0 + TILE, total_items);
-        const int nnz0 = (int)(d0 - row0), nnz1 = (int)(d1 - row1);
-        st.desc[0] = row0;
-        st.desc[1] = row1;
-        st.desc[2] = nnz0;
-        st.desc[3] = nnz1;
-        // nonzeros [nnz0, nnz1): bulk-copy the 16-byte-aligned cover, scalar-copy what sticks out past the
-        // last aligned element of the arrays (only ever the final tile)
+    // lane 0: stage chunk c into ring slot b
+    auto issue = [&](int b, int nnz0, int nnz1) {
+        // bulk-copy the 16-byte-aligned cover of [nnz0, nnz1); whatever sticks out past the last aligned
+        // element of the arrays (only in the matrix's final chunk) is copied with plain loads
         const int a0 = nnz0 & ~3;
         long long a1 = ((long long)nnz1 + 3) & ~3LL;
         const long long amax = a.nnz & ~3LL;
@@ -190,87 +343,77 @@ __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const SpmvArgs a) {
         if (a1 < a0) a1 = a0;
         const uint32_t ncopy = (uint32_t)(a1 - a0);
         for (long long k = a1; k < nnz1; ++k) {
-            st.cols[k - a0] = a.colids[k];
-            st.vals[k - a0] = a.values[k];
+            bufs[b].cols[k - a0] = a.colids[k];
+            bufs[b].vals[k - a0] = a.values[k];
         }
-        // rowptr[row0 .. min(row1+1, rows)]
-        const int r0 = row0 & ~3;
-        const int rend = min(row1 + 1, a.rows) + 1;  // one past the last needed entry
-        long long r1 = ((long long)rend + 3) & ~3LL;
-        const long long rmax = ((long long)a.rows + 1) & ~3LL;
-        if (r1 > rmax) r1 = rmax;
-        if (r1 < r0) r1 = r0;
-        const uint32_t nrp = (uint32_t)(r1 - r0);
-        for (long long k = r1; k < rend; ++k) st.rp[k - r0] = a.rowptr[k];
-        mbar_arrive_expect_tx(&full[stage], ncopy * 12u + nrp * 4u);
+        mbar_arrive_expect_tx(&bar[b], ncopy * 12u);
         if (ncopy) {
-            bulk_g2s(st.vals, a.values + a0, ncopy * 8u, &full[stage], policy);
-            bulk_g2s(st.cols, a.colids + a0, ncopy * 4u, &full[stage], policy);
+            bulk_g2s(bufs[b].vals, a.values + a0, ncopy * 8u, &bar[b], policy);
+            bulk_g2s(bufs[b].cols, a.colids + a0, ncopy * 4u, &bar[b], policy);
         }
-        if (nrp) bulk_g2s(st.rp, a.rowptr + r0, nrp * 4u, &full[stage], policy);
     };
 
-    if (tid == 0) {
+    const int wglobal = blockIdx.x * WARPS + warp;
+    const int stride = gridDim.x * WARPS;
+    if (lane == 0) {
         policy = policy_evict_first();
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int b = 0; b < NBUF; ++b) mbar_init(&bar[b], 1);
         fence_mbar_init();
-        n_long = 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < a.ntiles) issue(s, tile);
+        for (int b = 0; b < NBUF; ++b) {
+            const long long c = (long long)wglobal + (long long)b * stride;
+            if (c < a.nchunks) issue(b, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
         }
     }
+    __syncwarp();
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t parity = (it / STAGES) & 1;
-        mbar_wait(&full[stage], parity);
-        const SpmvStage<TILE> &st = stages[stage];
-
-        int lg = a.lanes_log2;
-        if (lg < 0) {  // automatic: about 4 nonzeros per lane
-            const int R1 = st.desc[1] - st.desc[0] + 1;
-            const int avg = (st.desc[3] - st.desc[2]) / R1;
-            lg = avg <= 6 ? 0 : avg <= 12 ? 1 : avg <= 24 ? 2 : avg <= 48 ? 3 : avg <= 96 ? 4 : 5;
+    for (long long c = wglobal; c < a.nchunks; c += stride, ++it) {
+        const int b = it % NBUF;
+        const uint32_t parity = (it / NBUF) & 1;
+        const int2 d0 = __ldg(a.desc + c), d1 = __ldg(a.desc + c + 1);
+        const int lg = a.force_lg >= 0 ? a.force_lg : (int)__ldg(a.lanes_lg + c);
+        // loads that do not depend on the staged data go out before the wait: this chunk's row pointers
+        // and the descriptor of the chunk that will reuse this ring slot
+        const int nloc = d1.x > d0.x ? d1.x - d0.x : 1;
+        int rp0 = 0, rp1 = 0;
+        if ((lane >> lg) < nloc) {
+            rp0 = __ldg(a.rowptr + d0.x + (lane >> lg));
+            rp1 = __ldg(a.rowptr + d0.x + (lane >> lg) + 1);
         }
+        const long long next = c + (long long)NBUF * stride;
+        int2 n0 = make_int2(0, 0), n1 = n0;
+        if (lane == 0 && next < a.nchunks) {
+            n0 = __ldg(a.desc + next);
+            n1 = __ldg(a.desc + next + 1);
+        }
+        mbar_wait(&bar[b], parity);
+        const ChunkBuf<CAP> &buf = bufs[b];
         switch (lg) {
-            case 0: tile_rows<TILE, THREADS, 1, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
-            case 1: tile_rows<TILE, THREADS, 2, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
-            case 2: tile_rows<TILE, THREADS, 4, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
-            case 3: tile_rows<TILE, THREADS, 8, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
-            case 4: tile_rows<TILE, THREADS, 16, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
-            default: tile_rows<TILE, THREADS, 32, ACCUM>(st, a, tile, long_rows, &n_long, red); break;
+            case 0: chunk_rows<1, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            case 1: chunk_rows<2, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            case 2: chunk_rows<4, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            case 3: chunk_rows<8, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            case 4: chunk_rows<16, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            default: chunk_rows<32, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
         }
-        // tile_rows ends with every thread past its last read of the stage (it syncs before the long-row
-        // sweep and after each swept row); one more barrier covers the no-long-row path
-        __syncthreads();
-        if (tid == 0) {
-            n_long = 0;
-            const int next = tile + STAGES * gridDim.x;
-            if (next < a.ntiles) issue(stage, next);
-        }
+        __syncwarp();  // every lane is done reading slot b
+        if (lane == 0 && next < a.nchunks) issue(b, n0.y, n1.y);
     }
 }
 
-// carry[t] belongs to row tile_row[t+1]; consecutive tiles inside one long row form a chain that one
-// thread adds up in tile order.
-__global__ void spmv_fixup_kernel(const int *__restrict__ tile_row, const double *__restrict__ carry,
-                                  const int *__restrict__ row_map, double *__restrict__ y, int ntiles, int rows) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const int row = tile_row[t + 1];
-    if (row >= rows) return;
-    if (t > 0 && tile_row[t] == row) return;  // not the head of its chain
-    double s = carry[t];
-    for (int u = t + 1; u < ntiles && tile_row[u + 1] == row; ++u) s += carry[u];
-    y[row_map ? row_map[row] : row] += s;
+// y[row] += carries of the row's non-final pieces, in piece order
+__global__ void spmv_long_fixup_kernel(const int4 *__restrict__ long_rows, int n_long,
+                                       const double *__restrict__ carry, const int *__restrict__ row_map,
+                                       double *__restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_long) return;
+    const int4 lr = long_rows[i];
+    double s = 0.0;
+    for (int p = 0; p < lr.z - 1; ++p) s += carry[lr.y + p];
+    y[row_map ? row_map[lr.x] : lr.x] += s;
 }
 
-// Baseline kernel kept for comparison and for tiny matrices: one warp per row straight from global memory.
+// Baseline kept for comparison: one warp per row straight from global memory, no staging.
 __global__ void spmv_warp_row_kernel(const int *__restrict__ rowptr, const int *__restrict__ colids,
                                      const double *__restrict__ values, const double *__restrict__ x,
                                      double *__restrict__ y, int rows) {
@@ -289,46 +432,79 @@ __global__ void spmv_warp_row_kernel(const int *__restrict__ rowptr, const int *
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-template <int TILE, int STAGES, int THREADS>
-static int launch_tile_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm, cudaStream_t stream) {
-    const size_t smem = sizeof(SpmvStage<TILE>) * STAGES;
-    auto k0 = spmv_tile_kernel<TILE, STAGES, THREADS, false>;
-    auto k1 = spmv_tile_kernel<TILE, STAGES, THREADS, true>;
+template <int CAP, int NBUF, int WARPS>
+static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm, cudaStream_t stream) {
+    const size_t smem = sizeof(ChunkBuf<CAP>) * NBUF * WARPS;
+    auto k0 = spmv_chunk_kernel<CAP, NBUF, WARPS, false>;
+    auto k1 = spmv_chunk_kernel<CAP, NBUF, WARPS, true>;
     static bool configured = false;
     if (!configured) {
         G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    int grid = std::min(args.ntiles, sm_count() * ctas_per_sm);
+    long long want = ((long long)args.nchunks + WARPS - 1) / WARPS;
+    int grid = (int)std::min<long long>(want, (long long)sm_count() * ctas_per_sm);
     if (grid < 1) grid = 1;
-    if (accum) k1<<<grid, THREADS, smem, stream>>>(args);
-    else k0<<<grid, THREADS, smem, stream>>>(args);
-    G4S_CHECK_LAUNCH("spmv_tile_kernel");
+    if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args);
+    else k0<<<grid, WARPS * 32, smem, stream>>>(args);
+    G4S_CHECK_LAUNCH("spmv_chunk_kernel");
     return G4S_OK;
 }
 
+constexpr int SPMV_CAP = 1024;
+
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream) {
     SpmvPlan &p = h->plan;
-    if (p.tile_row) return G4S_OK;
-    p.tile_items = 2048;
-    const long long items = (long long)h->rows + h->nnz;
-    p.ntiles = (int)((items + p.tile_items - 1) / p.tile_items);
-    if (p.ntiles < 1) p.ntiles = 1;
-    G4S_CUDA(cudaMalloc(&p.tile_row, sizeof(int) * ((size_t)p.ntiles + 1)));
-    G4S_CUDA(cudaMalloc(&p.carry, sizeof(double) * (size_t)p.ntiles));
-    G4S_CUDA(cudaMemsetAsync(p.carry, 0, sizeof(double) * (size_t)p.ntiles, stream));
-    const int threads = 256;
-    spmv_tile_search_kernel<<<(p.ntiles + 1 + threads - 1) / threads, threads, 0, stream>>>(
-        h->rowptr, h->rows, h->nnz, p.tile_items, p.ntiles, p.tile_row);
-    G4S_CHECK_LAUNCH("spmv_tile_search_kernel");
+    if (p.desc) return G4S_OK;
+    p.cap = SPMV_CAP;
+    const int nblocks = (h->rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
+    int *counts = nullptr, *stats = nullptr;
+    G4S_CUDA(cudaMalloc(&counts, sizeof(int) * ((size_t)nblocks + 1)));
+    G4S_CUDA(cudaMalloc(&stats, sizeof(int) * 4));
+    G4S_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, stream));
+    const int threads = 128;
+    count_long_rows_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->rows, p.cap, stats, stats + 1);
+    G4S_CHECK_LAUNCH("count_long_rows_kernel");
+    chunk_walk_kernel<false><<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(
+        h->rowptr, h->rows, p.cap, nblocks, counts, nullptr, nullptr, nullptr, nullptr);
+    G4S_CHECK_LAUNCH("chunk_walk_kernel<count>");
+    long long total = 0;
+    int rc = exclusive_scan_i32(counts, counts, nblocks, 0, &total, stream);
+    if (rc) return rc;
+    int hstats[4];
+    G4S_CUDA(cudaMemcpy(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost));
+    if (total > 2147483000LL) return fail(G4S_ERR_INVALID, "spmv plan: too many chunks");
+    p.nchunks = (int)total;
+    p.n_long = hstats[0];
+    p.max_row_len = hstats[1];
+    G4S_CUDA(cudaMalloc(&p.desc, sizeof(int2) * ((size_t)p.nchunks + 1)));
+    G4S_CUDA(cudaMalloc(&p.lanes_lg, (size_t)p.nchunks + 1));
+    G4S_CUDA(cudaMalloc(&p.carry, sizeof(double) * (size_t)std::max(p.nchunks, 1)));
+    G4S_CUDA(cudaMalloc(&p.long_rows, sizeof(int4) * (size_t)std::max(p.n_long, 1)));
+    G4S_CUDA(cudaMemsetAsync(p.carry, 0, sizeof(double) * (size_t)std::max(p.nchunks, 1), stream));
+    G4S_CUDA(cudaMemsetAsync(stats + 2, 0, sizeof(int), stream));
+    chunk_walk_kernel<true><<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(
+        h->rowptr, h->rows, p.cap, nblocks, counts, p.desc, p.lanes_lg, p.long_rows, stats + 2);
+    G4S_CHECK_LAUNCH("chunk_walk_kernel<fill>");
+    write_sentinel_kernel<<<1, 1, 0, stream>>>(p.desc, p.nchunks, h->rows, h->rowptr);
+    G4S_CHECK_LAUNCH("write_sentinel_kernel");
+    G4S_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(counts);
+    cudaFree(stats);
     return G4S_OK;
 }
 
 void spmv_free_plan(g4s_csr *h) {
-    if (h->plan.tile_row) cudaFree(h->plan.tile_row);
-    if (h->plan.carry) cudaFree(h->plan.carry);
-    h->plan = SpmvPlan();
+    SpmvPlan &p = h->plan;
+    if (p.desc) cudaFree(p.desc);
+    if (p.lanes_lg) cudaFree(p.lanes_lg);
+    if (p.carry) cudaFree(p.carry);
+    if (p.long_rows) cudaFree(p.long_rows);
+    const int lanes = p.lanes_per_row, variant = p.variant;
+    p = SpmvPlan();
+    p.lanes_per_row = lanes;
+    p.variant = variant;
 }
 
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream) {
@@ -338,8 +514,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     const SpmvPlan &p = h->plan;
     if (p.variant == 9) {  // comparison baseline
         if (accum || row_map) return fail(G4S_ERR_INVALID, "warp-per-row baseline supports plain y = A x only");
-        int grid = sm_count() * 8;
-        spmv_warp_row_kernel<<<grid, 256, 0, stream>>>(h->rowptr, h->colids, h->values, x, y, h->rows);
+        spmv_warp_row_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->colids, h->values, x, y, h->rows);
         G4S_CHECK_LAUNCH("spmv_warp_row_kernel");
         return G4S_OK;
     }
@@ -349,31 +524,35 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     a.values = h->values;
     a.x = x;
     a.y = y;
-    a.tile_row = p.tile_row;
+    a.desc = p.desc;
+    a.lanes_lg = p.lanes_lg;
     a.carry = p.carry;
     a.row_map = row_map;
     a.rows = h->rows;
     a.nnz = h->nnz;
-    a.ntiles = p.ntiles;
-    a.lanes_log2 = -1;
+    a.nchunks = p.nchunks;
+    a.force_lg = -1;
     if (p.lanes_per_row > 0) {
         int lg = 0;
         while ((1 << lg) < p.lanes_per_row && lg < 5) ++lg;
-        a.lanes_log2 = lg;
+        a.force_lg = lg;
     }
-    // variants: ring depth x CTAs per SM (TILE is fixed by the plan)
+    // kernel shapes: ring depth x warps per CTA x CTAs per SM.  Measured on B200, 3-D 27-point n=400
+    // (profiles/r01_spmv_sweep.txt): 18 single-buffered warps per SM as 2 CTAs of 9 is the fastest; deeper
+    // per-warp rings with fewer warps lose (resident warps, not per-warp prefetch depth, hide the latency).
     switch (p.variant) {
-        case 1: rc = launch_tile_kernel<2048, 2, 256>(a, accum, 3, stream); break;
-        case 2: rc = launch_tile_kernel<2048, 4, 256>(a, accum, 1, stream); break;
-        case 3: rc = launch_tile_kernel<2048, 3, 128>(a, accum, 2, stream); break;
-        case 4: rc = launch_tile_kernel<2048, 2, 512>(a, accum, 2, stream); break;
-        default: rc = launch_tile_kernel<2048, 3, 256>(a, accum, 2, stream); break;
+        case 1: rc = launch_chunk_kernel<SPMV_CAP, 1, 16>(a, accum, 1, stream); break;
+        case 2: rc = launch_chunk_kernel<SPMV_CAP, 2, 8>(a, accum, 1, stream); break;
+        case 3: rc = launch_chunk_kernel<SPMV_CAP, 2, 4>(a, accum, 2, stream); break;
+        case 4: rc = launch_chunk_kernel<SPMV_CAP, 1, 8>(a, accum, 2, stream); break;
+        case 5: rc = launch_chunk_kernel<SPMV_CAP, 1, 6>(a, accum, 3, stream); break;
+        default: rc = launch_chunk_kernel<SPMV_CAP, 1, 9>(a, accum, 2, stream); break;
     }
     if (rc) return rc;
-    const int threads = 256;
-    spmv_fixup_kernel<<<(p.ntiles + threads - 1) / threads, threads, 0, stream>>>(p.tile_row, p.carry, row_map, y,
-                                                                                 p.ntiles, h->rows);
-    G4S_CHECK_LAUNCH("spmv_fixup_kernel");
+    if (p.n_long > 0) {
+        spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, stream>>>(p.long_rows, p.n_long, p.carry, row_map, y);
+        G4S_CHECK_LAUNCH("spmv_long_fixup_kernel");
+    }
     return G4S_OK;
 }
 

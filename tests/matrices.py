@@ -6,6 +6,7 @@ import scipy.sparse as sp
 
 def to_tuple(m):
     m = sp.csr_matrix(m)
+    m.eliminate_zeros()  # sp.kron keeps explicit zeros of small dense factors
     m.sort_indices()
     return (m.shape[0], m.shape[1], m.indptr.astype(np.int32), m.indices.astype(np.int32),
             m.data.astype(np.float64))
