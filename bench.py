@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the G4S mv/mm hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, libg4s_b200.so)
+  python bench.py --impl reference [--gpus N] ...                the CPU arm (reference / oracle port)
+
+Headline workload = BASELINE.json configs[1]: SpMV y = A x on the 3-D 27-point Laplacian, n = 400
+(64 000 000 rows, 1 719 374 392 nnz, fp64 values, int32 indices), row-partitioned by nnz over N GPUs.
+A step is one SpMV.  metric = achieved GB/s on the ALGORITHMIC bytes 12 nnz + 4(rows+1) + 8 cols + 8 rows.
+The SpGEMM GFLOP/s of configs[3] (A x A, 2-D 5-point Laplacian, n = 2048) rides along in "spgemm" at N = 1.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 400                       # configs[1]
+SPGEMM_GRID = 2048                 # configs[3]
+CPU_SAMPLE_ROWS = 6_400_000        # 10 % of the rows: the bounded sample the CPU legs run on
+METRIC = "spmv_achieved_gbs"
+
+
+def spmv_bytes(rows, cols, nnz):
+    return 12.0 * nnz + 4.0 * (rows + 1) + 8.0 * cols + 8.0 * rows
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_spmv_sample(oracle, min_seconds, steps=None, warmup=1):
+    """The oracle's OpenMP CSR SpMV (port of "y = A x", mv/mv.c:23-27, on mm/inc/CSR.h's container — the
+    reference's own mv is dense MKL and cannot hold this matrix) on the first CPU_SAMPLE_ROWS rows of the
+    same 27-point matrix, all host threads.  Returns (GB/s, seconds per pass, description)."""
+    rows = CPU_SAMPLE_ROWS
+    A = oracle.gen_laplacian3d27(N_GRID, 0, rows)
+    ncols_touched = rows + N_GRID * N_GRID + N_GRID + 1  # x entries the sample reads
+    x = np.random.default_rng(12345).uniform(-1.0, 1.0, A[1])
+    nnz = len(A[3])
+    nbytes = 12.0 * nnz + 4.0 * (rows + 1) + 8.0 * ncols_touched + 8.0 * rows
+    for _ in range(warmup):
+        oracle.spmv_csr(A[2], A[3], A[4], x, omp=True)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle.spmv_csr(A[2], A[3], A[4], x, omp=True)
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and el >= min_seconds):
+            break
+    desc = ("rows [0,%d) of the n=%d 27-point Laplacian (%d nnz, %.2f GB algorithmic), %d passes of the "
+            "OpenMP CSR row loop" % (rows, N_GRID, nnz, nbytes / 1e9, n))
+    return nbytes * n / el / 1e9, el / n, desc
+
+
+def cpu_spgemm(ref, oracle, grid):
+    """Reference HashSpGEMM<false,true> (oracle/_ref) on configs[3]; falls back to the port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from matrices import laplacian_2d
+
+    A = laplacian_2d(grid)
+    total, _ = oracle.intprod(A[2], A[3], A[2])
+    if ref is not None and ref.available:
+        _, _, cnnz, secs = ref.hash_spgemm(A, A, variant=0, want_output=False)
+        kind, cores = "reference", ref.omp_max_threads()
+    else:
+        out = oracle.hash_spgemm(A, A, threads=oracle.omp_max_threads())
+        secs, kind, cores = out[3], "port", oracle.omp_max_threads()
+    return {"value": 2.0 * total / secs / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+            "sample": "full configs[3]: A x A, 2-D 5-point n=%d, one multiply (%.3f s)" % (grid, secs)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle.binding import Oracle
+
+    oracle = Oracle()
+    cores = oracle.omp_max_threads()
+    for _ in range(max(args.warmup - 1, 0)):
+        pass
+    gbs, sec, desc = cpu_spmv_sample(oracle, 0.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "SpMV y=Ax, 3-D 27-point Laplacian n=%d (BASELINE configs[1]); CPU arm runs a "
+                               "bounded sample per step" % N_GRID, "rows": N_GRID ** 3, "sample_rows": CPU_SAMPLE_ROWS},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world):
+    import torch
+
+    import g4s_b200
+    from g4s_b200 import lib
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L = lib()
+    if L.g4s_device_count() < 1:
+        raise RuntimeError("no CUDA device; g4s_b200 has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    rows_total = n ** 3
+    nnz_total = (3 * n - 2) ** 3
+    total_bytes = spmv_bytes(rows_total, rows_total, nnz_total)
+
+    if world == 1:
+        A = g4s_b200.CSR.laplacian3d27(n)
+        x_host = torch.empty(rows_total, dtype=torch.float64).pin_memory()
+        x_host.numpy()[:] = np.random.default_rng(12345).uniform(-1.0, 1.0, rows_total)
+        y_host = torch.empty(rows_total, dtype=torch.float64).pin_memory()
+        x = x_host.cuda(non_blocking=True)
+        y = torch.empty(rows_total, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+
+        def step():
+            A.spmv_device(x.data_ptr(), y.data_ptr())
+
+        def e2e_step():
+            A.spmv(x_host.numpy(), y_host.numpy())
+
+        h2d, d2h = 8 * rows_total, 8 * rows_total
+        launches_per_step = 1
+        parallelism = "1 GPU"
+    else:
+        from g4s_b200.dist import DistSpMV
+
+        op = DistSpMV.laplacian3d27(n, dist.group.WORLD)
+        x_host = torch.empty(op.local_rows, dtype=torch.float64).pin_memory()
+        x_host.numpy()[:] = np.random.default_rng(12345 + rank).uniform(-1.0, 1.0, op.local_rows)
+        y_host = torch.empty(op.local_rows, dtype=torch.float64).pin_memory()
+        x = x_host.cuda(non_blocking=True)
+        y = torch.empty(op.local_rows, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+
+        def step():
+            op.apply(x, y)
+
+        def e2e_step():
+            x.copy_(x_host, non_blocking=True)
+            op.apply(x, y)
+            y_host.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        h2d, d2h = 8 * rows_total, 8 * rows_total  # summed over ranks
+        launches_per_step = op.launches_per_step
+        parallelism = "rows cut by nnz over %d GPUs; halo of x exchanged over NCCL, overlapped with the " \
+                      "diagonal-block product" % world
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.g4s_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.g4s_kernel_launch_count() - launches0
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tl)
+        launches = int(tl.item())
+    ms_per_step = ms / args.steps
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # end to end through the host-pointer API: matrix resident (created once, like mkl_sparse_d_create_csr in
+    # the reference's mkl()), x from pinned host memory and y back to the host every step
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = total_bytes / (e2e_s / args.steps) / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel (spmv_chunk_kernel): algorithmic bytes of one launch over its mean
+    # duration inside the timed region (the fix-up / halo kernels are inside that time, so this is conservative)
+    per_gpu_bytes = total_bytes / world
+    achieved = per_gpu_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch") if world == 1 and n == N_GRID else None
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "SpMV y=Ax, 3-D 27-point Laplacian n=%d (BASELINE configs[1])" % n,
+                   "rows": rows_total, "nnz": nnz_total, "index_dtype": "int32", "bytes_per_step": total_bytes,
+                   "parallelism": parallelism, "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush"
+                   % (per_gpu_bytes / 1e9)},
+        "gflops": 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9,
+        "pct_of_8TBs": value / world / 8000.0 * 100.0,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "note": "matrix resident on the GPU (g4s_csr handle created once, as MKL's create_csr in the "
+                        "reference's mkl()); x uploaded from pinned host memory and y downloaded every step"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "spmv_chunk_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic},
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle.binding import Oracle, Ref
+
+        oracle = Oracle()
+        gbs, sec, desc = cpu_spmv_sample(oracle, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": oracle.omp_max_threads(), "kind": "port",
+                                "sample": desc}
+        if hasattr(L, "g4s_spgemm_device") and not args.no_spgemm:
+            line["spgemm"] = bench_spgemm(g4s_b200, torch, args)
+            try:
+                ref = Ref()
+            except Exception:
+                ref = None
+            line["spgemm"]["cpu_baseline"] = cpu_spgemm(ref, oracle, SPGEMM_GRID)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_spgemm(g4s_b200, torch, args):
+    """configs[3]: C = A A on the 2-D 5-point Laplacian n = 2048 (4 194 304 rows), device-timed, plus the
+    host-pointer mkl() entry end to end."""
+    import ctypes as C
+
+    A = g4s_b200.CSR.laplacian2d(SPGEMM_GRID)
+    flop = 2.0 * g4s_b200.compute_flop(A, A)
+    for _ in range(3):
+        g4s_b200.HashSpGEMM(A, A).make_empty()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        Cm = g4s_b200.HashSpGEMM(A, A)
+        nnzc = Cm.nnz
+        Cm.make_empty()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    phases = (C.c_double * 4)()
+    g4s_b200.lib().g4s_spgemm_last_phase_ms(phases)
+    nnza = A.nnz
+    rows = A.rows
+    nbytes = 2 * (12.0 * nnza + 4.0 * (rows + 1)) + 12.0 * nnzc + 4.0 * (rows + 1)
+    Ah = A.to_host()
+    t = g4s_b200.Timings()
+    g4s_b200.mkl(Ah, Ah, t)
+    t0 = time.perf_counter()
+    g4s_b200.mkl(Ah, Ah, t)
+    e2e_s = time.perf_counter() - t0
+    return {"metric": "spgemm_gflops", "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms": ms,
+            "config": {"workload": "SpGEMM C=A*A, 2-D 5-point Laplacian n=%d (BASELINE configs[3])" % SPGEMM_GRID,
+                       "rows": rows, "nnzA": nnza, "nnzC": nnzc, "flop": flop},
+            "phase_ms": {"binning": phases[0], "symbolic": phases[1], "scan_alloc": phases[2], "numeric": phases[3]},
+            "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "e2e": {"value": flop / e2e_s / 1e9, "unit": "GFLOP/s", "seconds": e2e_s,
+                    "h2d_bytes_per_step": 2 * (12 * nnza + 4 * (rows + 1)), "d2h_bytes_per_step": 12 * nnzc + 4 * (rows + 1),
+                    "timings": {k: getattr(t, k) for k in ("create", "spmm", "export_csr", "destroy", "total")}}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_GRID, help="grid edge (default 400 = BASELINE configs[1])")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget at N=1")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-spgemm", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        if world != args.gpus and world > 1:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

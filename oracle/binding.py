@@ -62,6 +62,7 @@ class Oracle:
             build()
         self.lib = L = C.CDLL(path)
         L.oracle_intprod.restype = C.c_longlong
+        L.oracle_laplacian3d27_nnz.restype = C.c_longlong
         L.oracle_hash_spgemm_omp.restype = C.c_double
         L.oracle_free.argtypes = [C.c_void_p]
 
@@ -86,6 +87,17 @@ class Oracle:
         y = np.empty(rows, dtype=np.float64)
         self.lib.oracle_spmv_csr_abs(C.c_int(rows), _ip(rowptr), _ip(colids), _dp(values), _dp(x), _dp(y))
         return y
+
+    def gen_laplacian3d27(self, n, row0=0, row1=None):
+        """Rows [row0,row1) of the 3-D 27-point Laplacian as (rows, cols, rowptr, colids, values)."""
+        row1 = n ** 3 if row1 is None else row1
+        nnz = int(self.lib.oracle_laplacian3d27_nnz(C.c_int(n), C.c_longlong(row0), C.c_longlong(row1)))
+        rowptr = np.empty(row1 - row0 + 1, dtype=np.int32)
+        colids = np.empty(nnz, dtype=np.int32)
+        values = np.empty(nnz, dtype=np.float64)
+        self.lib.oracle_gen_laplacian3d27(C.c_int(n), C.c_longlong(row0), C.c_longlong(row1), _ip(rowptr),
+                                          _ip(colids), _dp(values))
+        return (row1 - row0, n ** 3, rowptr, colids, values)
 
     def dense_mv(self, name, A, B):
         """name in dgemv|dsymv|dtrmv|dspmv; returns (B_after, C) like mv/mv.c's (A,B,C,dim) calls."""

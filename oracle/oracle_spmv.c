@@ -121,3 +121,40 @@ void oracle_bsr_spmm(int mb, int bs, const int *browptr, const int *bcolids, con
         }
     }
 }
+
+/* Synthetic input of BASELINE config 2 on the host (rows [row0,row1) of the 3-D 27-point Laplacian on an n^3
+ * grid, natural ordering, diag 26, off-diag -1, global column ids).  Written independently of the product's
+ * device generator so that tests can cross-check the two, and used by bench.py's CPU legs to build their
+ * bounded sample without touching the GPU. */
+static long long o_cnt(int n, long long t) { return 1 + (t > 0) + (t < n - 1); }
+long long oracle_laplacian3d27_nnz(int n, long long row0, long long row1) {
+    long long total = 0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+    for (long long row = row0; row < row1; ++row)
+        total += o_cnt(n, row % n) * o_cnt(n, (row / n) % n) * o_cnt(n, row / ((long long)n * n));
+    return total;
+}
+void oracle_gen_laplacian3d27(int n, long long row0, long long row1, int *rowptr, int *colids, double *values) {
+    const long long nrows = row1 - row0;
+    rowptr[0] = 0;
+    for (long long r = 0; r < nrows; ++r) { /* sequential prefix: the sample is a few million rows */
+        const long long row = row0 + r;
+        rowptr[r + 1] = rowptr[r] +
+                        (int)(o_cnt(n, row % n) * o_cnt(n, (row / n) % n) * o_cnt(n, row / ((long long)n * n)));
+    }
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < nrows; ++r) {
+        const long long row = row0 + r;
+        const int i = (int)(row % n), j = (int)((row / n) % n), k = (int)(row / ((long long)n * n));
+        long p = rowptr[r];
+        for (int dk = -1; dk <= 1; ++dk)
+            for (int dj = -1; dj <= 1; ++dj)
+                for (int di = -1; di <= 1; ++di) {
+                    if (k + dk < 0 || k + dk >= n || j + dj < 0 || j + dj >= n || i + di < 0 || i + di >= n) continue;
+                    const long long col = ((long long)(k + dk) * n + (j + dj)) * n + (i + di);
+                    colids[p] = (int)col;
+                    values[p] = col == row ? 26.0 : -1.0;
+                    ++p;
+                }
+    }
+}
