@@ -1,0 +1,655 @@
+// SpGEMM  C = A B  (CSR<int,double> x CSR<int,double> -> CSR<int,double>, sorted columns) for sm_100a.
+//
+// GPU restatement of the reference's two-phase hash SpGEMM:
+//   work count + size classes : BIN::set_intprod_num / set_bin_id   (mm/inc/BIN.h:77-95, :157-177)
+//   symbolic                  : hash_symbolic_kernel                 (mm/inc/hash_mult.h:64-109)
+//   row pointers              : scan(row_nz -> crpt)                 (mm/inc/hash_mult.h:506-507)
+//   numeric + sorted store    : hash_numeric + sort_and_store_table2mat (mm/inc/hash_mult.h:525-608)
+// and of the shipped driver's mkl() entry point (mm/inc/mkl_mult.h:40-110), whose output is the same sorted CSR.
+//
+// Where the reference gives each OpenMP thread one reusable table and walks rows one after another, the GPU
+// gives every ROW its own table, sized by the row's intermediate-product count w = min(work, cols):
+//   class 0  w == 0        nothing to do (row is empty)
+//   class 1  w <= 32       4 lanes per row, 32-slot table in shared memory (64 rows per CTA)
+//   class 2  w <= 256      one warp per row, 512 slots
+//   class 3  w <= 2048     one 256-thread CTA per row, 4096 slots
+//   class 4  w <= 8192     one 1024-thread CTA per row, 8192 slots
+//   class 5  larger        one CTA per row, power-of-two table in global memory (persistent CTAs own a slab)
+// Hash = (key * 107) & (size-1) with linear probing, empty = -1, exactly the reference's function
+// (hash_mult.h:23, :89-101); insertion uses atomicCAS on the key and atomicAdd(double) on the value, so the
+// accumulation order inside a row differs from the reference's sequential order (values agree to rounding;
+// the sparsity pattern is exact).  Rows are handed out class by class in ascending row order so that
+// neighbouring rows of B stay hot in L1/L2.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace g4s {
+
+int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, long long *total_host,
+                       cudaStream_t stream);
+int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz);
+
+constexpr int NCLASS = 6;
+constexpr int HASH_MULT = 107;  // mm/inc/hash_mult.h:23
+
+__host__ __device__ inline int work_class(int work, int cols) {
+    const int w = work < cols ? work : cols;
+    if (w == 0) return 0;
+    if (w <= 32) return 1;
+    if (w <= 256) return 2;
+    if (w <= 2048) return 3;
+    if (w <= 8192) return 4;
+    return 5;
+}
+
+// ---- per-row work (BIN::set_intprod_num) + class histogram ----------------------------------------------
+__global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restrict__ acol,
+                                const int *__restrict__ brpt, int M, int cols, int *__restrict__ row_work,
+                                unsigned long long *__restrict__ total, int *__restrict__ class_count) {
+    __shared__ int hist[NCLASS];
+    __shared__ unsigned long long bsum;
+    if (threadIdx.x < NCLASS) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) bsum = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    long long w = 0;
+    if (i < M) {
+        for (int j = __ldg(arpt + i); j < __ldg(arpt + i + 1); ++j) {
+            const int k = __ldg(acol + j);
+            w += __ldg(brpt + k + 1) - __ldg(brpt + k);
+        }
+        const int wi = w > 2147483647LL ? 2147483647 : (int)w;
+        if (row_work) row_work[i] = wi;
+        if (class_count) atomicAdd(&hist[work_class(wi, cols)], 1);
+    }
+    unsigned long long s = (unsigned long long)w;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&bsum, s);
+    __syncthreads();
+    if (threadIdx.x == 0 && bsum) atomicAdd(total, bsum);
+    if (class_count && threadIdx.x < NCLASS && hist[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+}
+
+// rows of each class, ascending inside a block of 256 rows; blocks reserve their ranges with one atomic per class
+__global__ void bin_fill_kernel(const int *__restrict__ row_work, int M, int cols, int *__restrict__ cursor,
+                                int *__restrict__ perm, int *__restrict__ row_nnz) {
+    __shared__ int wcount[NCLASS][8];
+    __shared__ int base[NCLASS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = i < M ? work_class(row_work[i], cols) : -1;
+    if (c == 0) row_nnz[i] = 0;
+    int my_rank = 0;
+#pragma unroll
+    for (int k = 1; k < NCLASS; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, c == k);
+        if (c == k) my_rank = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) wcount[k][w] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLASS && threadIdx.x > 0) {
+        int tot = 0;
+        for (int q = 0; q < 8; ++q) {
+            const int t = wcount[threadIdx.x][q];
+            wcount[threadIdx.x][q] = tot;
+            tot += t;
+        }
+        base[threadIdx.x] = tot ? atomicAdd(&cursor[threadIdx.x], tot) : 0;
+    }
+    __syncthreads();
+    if (c > 0) perm[base[c] + wcount[c][w] + my_rank] = i;
+}
+
+// ---- hash kernels -----------------------------------------------------------------------------------------
+struct SpgemmArgs {
+    const int *arpt, *acol;
+    const double *aval;
+    const int *brpt, *bcol;
+    const double *bval;
+    int M, N;
+    const int *crpt;
+    int *ccol;
+    double *cval;
+    int *row_nnz;
+    int sub_lg;  // lanes cooperating on one row of B (log2), chosen from B's mean row length
+};
+
+template <int GROUP>
+__device__ __forceinline__ void group_sync() {
+    if (GROUP <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+// insert key into a power-of-two table; returns true when the key was new
+__device__ __forceinline__ bool hash_insert(int *keys, int mask, int key) {
+    int h = (key * HASH_MULT) & mask;
+    for (;;) {
+        const int cur = keys[h];
+        if (cur == key) return false;
+        if (cur == -1) {
+            const int old = atomicCAS(&keys[h], -1, key);
+            if (old == -1) return true;
+            if (old == key) return false;
+        }
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ void hash_accumulate(int *keys, double *vals, int mask, int key, double v) {
+    int h = (key * HASH_MULT) & mask;
+    for (;;) {
+        const int cur = keys[h];
+        if (cur == key) break;
+        if (cur == -1) {
+            const int old = atomicCAS(&keys[h], -1, key);
+            if (old == -1 || old == key) break;
+        }
+        h = (h + 1) & mask;
+    }
+    atomicAdd(&vals[h], v);
+}
+
+// GROUP lanes own one row; TABLE slots; WMAX bounds the row's nonzeros (compaction buffer).
+template <int GROUP, int TABLE, int WMAX, int THREADS, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a, const int *__restrict__ list,
+                                                               int nlist) {
+    constexpr int RPC = THREADS / GROUP;
+    extern __shared__ __align__(16) unsigned char sm[];
+    double *vals = reinterpret_cast<double *>(sm);                        // [RPC][TABLE]   (numeric)
+    double *cvals = vals + (NUMERIC ? RPC * TABLE : 0);                   // [RPC][WMAX]    (numeric)
+    int *keys = reinterpret_cast<int *>(cvals + (NUMERIC ? RPC * WMAX : 0));  // [RPC][TABLE]
+    int *ckeys = keys + RPC * TABLE;                                      // [RPC][WMAX]    (numeric)
+    int *cnt = ckeys + (NUMERIC ? RPC * WMAX : 0);                        // [RPC]
+    const int g = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;
+    int *mykeys = keys + g * TABLE;
+    double *myvals = vals + g * TABLE;
+    int sub_lg = a.sub_lg;
+    while ((1 << sub_lg) > GROUP) --sub_lg;
+    const int SUB = 1 << sub_lg, nsub = GROUP >> sub_lg, my_sub = lane >> sub_lg, sl = lane & (SUB - 1);
+
+    for (int base = blockIdx.x * RPC; base < nlist; base += gridDim.x * RPC) {
+        const int idx = base + g;
+        const int row = idx < nlist ? __ldg(list + idx) : -1;
+        for (int s = lane; s < TABLE; s += GROUP) {
+            mykeys[s] = -1;
+            if (NUMERIC) myvals[s] = 0.0;
+        }
+        if (lane == 0) cnt[g] = 0;
+        group_sync<GROUP>();
+        int fresh = 0;
+        if (row >= 0) {
+            const int as = __ldg(a.arpt + row), ae = __ldg(a.arpt + row + 1);
+            for (int j = as + my_sub; j < ae; j += nsub) {
+                const int k = __ldg(a.acol + j);
+                const int bs = __ldg(a.brpt + k), be = __ldg(a.brpt + k + 1);
+                if (NUMERIC) {
+                    const double av = __ldg(a.aval + j);
+                    for (int p = bs + sl; p < be; p += SUB)
+                        hash_accumulate(mykeys, myvals, TABLE - 1, __ldg(a.bcol + p), av * __ldg(a.bval + p));
+                } else {
+                    for (int p = bs + sl; p < be; p += SUB) fresh += hash_insert(mykeys, TABLE - 1, __ldg(a.bcol + p));
+                }
+            }
+        }
+        if (!NUMERIC) {
+            if (GROUP <= 32) {
+#pragma unroll
+                for (int o = GROUP >> 1; o; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+                if (lane == 0 && row >= 0) a.row_nnz[row] = fresh;
+            } else {
+                if (fresh) atomicAdd(&cnt[g], fresh);
+                __syncthreads();
+                if (lane == 0 && row >= 0) a.row_nnz[row] = cnt[g];
+            }
+            group_sync<GROUP>();
+        } else {
+            group_sync<GROUP>();
+            // compact the occupied slots, then rank-sort by column straight into C's row
+            int *myck = ckeys + g * WMAX;
+            double *mycv = cvals + g * WMAX;
+            for (int s = lane; s < TABLE; s += GROUP) {
+                const int key = mykeys[s];
+                if (key != -1) {
+                    const int pos = atomicAdd(&cnt[g], 1);
+                    myck[pos] = key;
+                    mycv[pos] = myvals[s];
+                }
+            }
+            group_sync<GROUP>();
+            if (row >= 0) {
+                const int n = cnt[g];
+                const int out = __ldg(a.crpt + row);
+                for (int e = lane; e < n; e += GROUP) {
+                    const int key = myck[e];
+                    int rank = 0;
+                    for (int f = 0; f < n; ++f) rank += myck[f] < key;
+                    a.ccol[out + rank] = key;
+                    a.cval[out + rank] = mycv[e];
+                }
+            }
+            group_sync<GROUP>();
+        }
+    }
+}
+
+// class 5: tables in global memory.  Persistent CTAs; CTA b owns slab b (slab_slots entries) and re-initialises
+// only the power-of-two prefix the current row needs.
+template <bool NUMERIC>
+__global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a, const int *__restrict__ list,
+                                                              int nlist, const int *__restrict__ row_work,
+                                                              int *__restrict__ slab_keys,
+                                                              double *__restrict__ slab_vals, long long slab_slots) {
+    __shared__ int cnt;
+    int *keys = slab_keys + (long long)blockIdx.x * slab_slots;
+    double *vals = NUMERIC ? slab_vals + (long long)blockIdx.x * slab_slots : nullptr;
+    int sub_lg = a.sub_lg;
+    const int SUB = 1 << sub_lg, nsub = blockDim.x >> sub_lg, my_sub = threadIdx.x >> sub_lg,
+              sl = threadIdx.x & (SUB - 1);
+    for (int idx = blockIdx.x; idx < nlist; idx += gridDim.x) {
+        const int row = list[idx];
+        const int w = min(row_work[row], a.N);
+        long long tsize = 16384;
+        while (tsize < 2LL * w) tsize <<= 1;
+        if (tsize > slab_slots) tsize = slab_slots;
+        const int mask = (int)(tsize - 1);
+        for (long long s = threadIdx.x; s < tsize; s += blockDim.x) {
+            keys[s] = -1;
+            if (NUMERIC) vals[s] = 0.0;
+        }
+        if (threadIdx.x == 0) cnt = 0;
+        __syncthreads();
+        int fresh = 0;
+        const int as = a.arpt[row], ae = a.arpt[row + 1];
+        for (int j = as + my_sub; j < ae; j += nsub) {
+            const int k = a.acol[j];
+            const int bs = a.brpt[k], be = a.brpt[k + 1];
+            if (NUMERIC) {
+                const double av = a.aval[j];
+                for (int p = bs + sl; p < be; p += SUB) hash_accumulate(keys, vals, mask, a.bcol[p], av * a.bval[p]);
+            } else {
+                for (int p = bs + sl; p < be; p += SUB) fresh += hash_insert(keys, mask, a.bcol[p]);
+            }
+        }
+        if (!NUMERIC) {
+            if (fresh) atomicAdd(&cnt, fresh);
+            __syncthreads();
+            if (threadIdx.x == 0) a.row_nnz[row] = cnt;
+            __syncthreads();
+        } else {
+            __syncthreads();
+            const int out = a.crpt[row];
+            const int n = a.crpt[row + 1] - out;
+            for (long long s = threadIdx.x; s < tsize; s += blockDim.x) {
+                const int key = keys[s];
+                if (key != -1) {
+                    const int pos = atomicAdd(&cnt, 1);
+                    a.ccol[out + pos] = key;
+                    a.cval[out + pos] = vals[s];
+                }
+            }
+            __syncthreads();
+            // in-place bitonic sort of the row in global memory.  Normalised network (every compare-exchange
+            // puts the smaller key at the lower index), so the virtual +inf padding beyond n never moves.
+            int n2 = 1;
+            while (n2 < n) n2 <<= 1;
+            int *ck = a.ccol + out;
+            double *cv = a.cval + out;
+            auto cas = [&](int t, int u) {
+                if (u > t && u < n) {
+                    const int kt = ck[t], ku = ck[u];
+                    if (kt > ku) {
+                        ck[t] = ku;
+                        ck[u] = kt;
+                        const double vt = cv[t];
+                        cv[t] = cv[u];
+                        cv[u] = vt;
+                    }
+                }
+            };
+            for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+                for (int t = threadIdx.x; t < n; t += blockDim.x) cas(t, t ^ (k2 - 1));
+                __syncthreads();
+                for (int j2 = k2 >> 2; j2 > 0; j2 >>= 1) {
+                    for (int t = threadIdx.x; t < n; t += blockDim.x) cas(t, t ^ j2);
+                    __syncthreads();
+                }
+            }
+        }
+    }
+}
+
+static thread_local double t_phase_ms[4] = {0, 0, 0, 0};
+
+template <int GROUP, int TABLE, int WMAX, int THREADS>
+static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
+    if (nlist == 0) return G4S_OK;
+    constexpr int RPC = THREADS / GROUP;
+    const size_t smem_sym = sizeof(int) * (RPC * TABLE + RPC) + 16;
+    const size_t smem_num = sizeof(double) * (RPC * TABLE + RPC * WMAX) + sizeof(int) * (RPC * TABLE + RPC * WMAX + RPC) + 16;
+    auto ks = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, false>;
+    auto kn = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, true>;
+    static bool configured = false;
+    if (!configured) {
+        G4S_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sym));
+        G4S_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_num));
+        configured = true;
+    }
+    const long long want = ((long long)nlist + RPC - 1) / RPC;
+    const int grid = (int)std::min<long long>(want, (long long)sm_count() * 16);
+    if (numeric) kn<<<grid, THREADS, smem_num, stream>>>(a, list, nlist);
+    else ks<<<grid, THREADS, smem_sym, stream>>>(a, list, nlist);
+    G4S_CHECK_LAUNCH("spgemm_smem_kernel");
+    return G4S_OK;
+}
+
+struct Bins {
+    int *row_work = nullptr;
+    int *perm = nullptr;
+    int count[NCLASS] = {0};
+    int offset[NCLASS + 1] = {0};
+    long long total_work = 0;
+    int max_work = 0;
+};
+
+static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab_keys, double *slab_vals,
+                     long long slab_slots, int slab_ctas, cudaStream_t stream) {
+    int rc;
+    if ((rc = launch_smem<4, 32, 32, 256>(a, b.perm + b.offset[1], b.count[1], numeric, stream))) return rc;
+    if ((rc = launch_smem<32, 512, 256, 256>(a, b.perm + b.offset[2], b.count[2], numeric, stream))) return rc;
+    if ((rc = launch_smem<256, 4096, 2048, 256>(a, b.perm + b.offset[3], b.count[3], numeric, stream))) return rc;
+    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, b.perm + b.offset[4], b.count[4], numeric, stream))) return rc;
+    if (b.count[5]) {
+        if (numeric)
+            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, b.perm + b.offset[5], b.count[5], b.row_work,
+                                                                      slab_keys, slab_vals, slab_slots);
+        else
+            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, b.perm + b.offset[5], b.count[5], b.row_work,
+                                                                       slab_keys, slab_vals, slab_slots);
+        G4S_CHECK_LAUNCH("spgemm_global_kernel");
+    }
+    return G4S_OK;
+}
+
+__global__ void max_work_kernel(const int *__restrict__ row_work, int M, int *__restrict__ out) {
+    int m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, row_work[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
+    if (A->cols != B->rows) return fail(G4S_ERR_SHAPE, "g4s_spgemm: A.cols != B.rows");
+    const int M = A->rows, N = B->cols;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
+    G4S_CUDA(cudaEventRecord(ev[0], stream));
+
+    // ---- binning --------------------------------------------------------------------------------------
+    Bins b;
+    int *dcount = nullptr;  // [NCLASS] counts, [NCLASS] cursors, [1] max
+    unsigned long long *dtotal = nullptr;
+    int *row_nnz = nullptr;
+    G4S_CUDA(cudaMallocAsync(&b.row_work, sizeof(int) * (size_t)std::max(M, 1), stream));
+    G4S_CUDA(cudaMallocAsync(&b.perm, sizeof(int) * (size_t)std::max(M, 1), stream));
+    G4S_CUDA(cudaMallocAsync(&row_nnz, sizeof(int) * ((size_t)M + 1), stream));
+    G4S_CUDA(cudaMallocAsync(&dcount, sizeof(int) * (2 * NCLASS + 1), stream));
+    G4S_CUDA(cudaMallocAsync(&dtotal, sizeof(unsigned long long), stream));
+    G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int) * (2 * NCLASS + 1), stream));
+    G4S_CUDA(cudaMemsetAsync(dtotal, 0, sizeof(unsigned long long), stream));
+    const int threads = 256;
+    const int blocks = (M + threads - 1) / threads;
+    if (M > 0) {
+        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, dtotal, dcount);
+        G4S_CHECK_LAUNCH("row_work_kernel");
+        max_work_kernel<<<sm_count() * 4, 256, 0, stream>>>(b.row_work, M, dcount + 2 * NCLASS);
+        G4S_CHECK_LAUNCH("max_work_kernel");
+    }
+    int hcount[2 * NCLASS + 1];
+    unsigned long long htotal = 0;
+    G4S_CUDA(cudaMemcpyAsync(hcount, dcount, sizeof(hcount), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaMemcpyAsync(&htotal, dtotal, sizeof(htotal), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaStreamSynchronize(stream));
+    b.total_work = (long long)htotal;
+    b.max_work = hcount[2 * NCLASS];
+    for (int c = 0; c < NCLASS; ++c) {
+        b.count[c] = hcount[c];
+        b.offset[c + 1] = b.offset[c] + (c ? hcount[c] : 0);
+    }
+    b.offset[0] = 0;
+    {   // cursors start at each class's offset (class 0 rows are not listed)
+        int cur[NCLASS];
+        int off = 0;
+        for (int c = 0; c < NCLASS; ++c) {
+            cur[c] = off;
+            b.offset[c] = off;
+            if (c) off += b.count[c];
+        }
+        b.offset[NCLASS] = off;
+        b.offset[0] = 0;
+        G4S_CUDA(cudaMemcpyAsync(dcount + NCLASS, cur, sizeof(cur), cudaMemcpyHostToDevice, stream));
+    }
+    if (M > 0) {
+        bin_fill_kernel<<<blocks, threads, 0, stream>>>(b.row_work, M, N, dcount + NCLASS, b.perm, row_nnz);
+        G4S_CHECK_LAUNCH("bin_fill_kernel");
+    }
+    G4S_CUDA(cudaEventRecord(ev[1], stream));
+
+    // lanes per row of B: next power of two >= B's mean row length
+    int sub_lg = 0;
+    {
+        const double avg = B->rows ? (double)B->nnz / B->rows : 1.0;
+        while ((1 << sub_lg) < avg && sub_lg < 5) ++sub_lg;
+    }
+    // global-memory slabs for class 5
+    int *slab_keys = nullptr;
+    double *slab_vals = nullptr;
+    long long slab_slots = 0;
+    int slab_ctas = 0;
+    if (b.count[5]) {
+        const long long w = std::min<long long>(b.max_work, N);
+        slab_slots = 16384;
+        while (slab_slots < 2 * w) slab_slots <<= 1;
+        const long long budget = 2LL << 30;  // bytes of scratch
+        slab_ctas = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 2, budget / (slab_slots * 12)));
+        slab_ctas = std::min(slab_ctas, b.count[5]);
+        G4S_CUDA(cudaMallocAsync(&slab_keys, sizeof(int) * (size_t)slab_slots * slab_ctas, stream));
+        G4S_CUDA(cudaMallocAsync(&slab_vals, sizeof(double) * (size_t)slab_slots * slab_ctas, stream));
+    }
+
+    SpgemmArgs a;
+    a.arpt = A->rowptr;
+    a.acol = A->colids;
+    a.aval = A->values;
+    a.brpt = B->rowptr;
+    a.bcol = B->colids;
+    a.bval = B->values;
+    a.M = M;
+    a.N = N;
+    a.crpt = nullptr;
+    a.ccol = nullptr;
+    a.cval = nullptr;
+    a.row_nnz = row_nnz;
+    a.sub_lg = sub_lg;
+
+    // ---- symbolic ---------------------------------------------------------------------------------------
+    int rc = run_phase(a, b, false, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
+    if (rc) return rc;
+    G4S_CUDA(cudaEventRecord(ev[2], stream));
+
+    // ---- row pointers + allocation ------------------------------------------------------------------------
+    long long cnnz = 0;
+    int *crpt_tmp = nullptr;
+    G4S_CUDA(cudaMallocAsync(&crpt_tmp, sizeof(int) * ((size_t)M + 1), stream));
+    rc = exclusive_scan_i32(row_nnz, crpt_tmp, M, 1, &cnnz, stream);
+    if (rc) return rc;
+    if (cnnz > 2147483647LL) return fail(G4S_ERR_INVALID, "g4s_spgemm: nnz(C) exceeds int32 row pointers");
+    g4s_csr *C = nullptr;
+    rc = alloc_csr(&C, M, N, cnnz);
+    if (rc) return rc;
+    G4S_CUDA(cudaMemcpyAsync(C->rowptr, crpt_tmp, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToDevice, stream));
+    G4S_CUDA(cudaEventRecord(ev[3], stream));
+
+    // ---- numeric ------------------------------------------------------------------------------------------
+    a.crpt = C->rowptr;
+    a.ccol = C->colids;
+    a.cval = C->values;
+    rc = run_phase(a, b, true, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
+    if (rc) {
+        g4s_csr_destroy(C);
+        return rc;
+    }
+    G4S_CUDA(cudaEventRecord(ev[4], stream));
+
+    G4S_CUDA(cudaFreeAsync(crpt_tmp, stream));
+    if (slab_keys) G4S_CUDA(cudaFreeAsync(slab_keys, stream));
+    if (slab_vals) G4S_CUDA(cudaFreeAsync(slab_vals, stream));
+    G4S_CUDA(cudaFreeAsync(b.row_work, stream));
+    G4S_CUDA(cudaFreeAsync(b.perm, stream));
+    G4S_CUDA(cudaFreeAsync(row_nnz, stream));
+    G4S_CUDA(cudaFreeAsync(dcount, stream));
+    G4S_CUDA(cudaFreeAsync(dtotal, stream));
+    G4S_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        t_phase_ms[i] = ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    *Cout = C;
+    return G4S_OK;
+}
+
+}  // namespace g4s
+
+using namespace g4s;
+
+extern "C" {
+
+int g4s_spgemm_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream) {
+    if (!A || !B || !C) return fail(G4S_ERR_INVALID, "g4s_spgemm_device: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return spgemm_run(A, B, C, (cudaStream_t)stream);
+}
+
+int g4s_spgemm_last_phase_ms(double *ms4) {
+    if (!ms4) return fail(G4S_ERR_INVALID, "null argument");
+    for (int i = 0; i < 4; ++i) ms4[i] = t_phase_ms[i];
+    return G4S_OK;
+}
+
+int g4s_compute_flop_device(g4s_csr_t A, g4s_csr_t B, long long *total, int *row_work_dev, void *stream_) {
+    if (!A || !B || !total) return fail(G4S_ERR_INVALID, "g4s_compute_flop_device: null argument");
+    if (A->cols != B->rows) return fail(G4S_ERR_SHAPE, "g4s_compute_flop_device: A.cols != B.rows");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *dtotal = nullptr;
+    G4S_CUDA(cudaMallocAsync(&dtotal, sizeof(unsigned long long), stream));
+    G4S_CUDA(cudaMemsetAsync(dtotal, 0, sizeof(unsigned long long), stream));
+    if (A->rows > 0) {
+        row_work_kernel<<<(A->rows + 255) / 256, 256, 0, stream>>>(A->rowptr, A->colids, B->rowptr, A->rows, B->cols,
+                                                                  row_work_dev, dtotal, nullptr);
+        G4S_CHECK_LAUNCH("row_work_kernel");
+    }
+    unsigned long long h = 0;
+    G4S_CUDA(cudaMemcpyAsync(&h, dtotal, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaStreamSynchronize(stream));
+    G4S_CUDA(cudaFreeAsync(dtotal, stream));
+    *total = (long long)h;
+    return G4S_OK;
+}
+
+long long compute_flop_host(const int *arpt, const int *acol, const int *brpt, int M) {
+    long long total = 0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+    for (int i = 0; i < M; ++i)
+        for (int j = arpt[i]; j < arpt[i + 1]; ++j) total += brpt[acol[j] + 1] - brpt[acol[j]];
+    return total;
+}
+
+static void *default_alloc(size_t bytes, void *) { return malloc(bytes ? bytes : 1); }
+
+int g4s_mkl_alloc(const int *arpt, const int *acol, const double *aval, const int *brpt, const int *bcol,
+                  const double *bval, int **crpt_, int **ccol_, double **cval_, int M, int K, int N, int *cnnz_,
+                  g4s_timings *timing, g4s_alloc_fn alloc_index, g4s_alloc_fn alloc_value, void *ctx) {
+    if (!arpt || !brpt || !crpt_ || !ccol_ || !cval_ || !cnnz_ || M < 0 || K < 0 || N < 0)
+        return fail(G4S_ERR_INVALID, "g4s_mkl: bad arguments");
+    if (!alloc_index) alloc_index = default_alloc;
+    if (!alloc_value) alloc_value = default_alloc;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    g4s_timings local;
+    g4s_timings *t = timing ? timing : &local;
+    const unsigned char ms = t->measure_separate, mt = t->measure_total;
+    g4s_timings_init(t);
+    if (timing) {
+        t->measure_separate = ms;
+        t->measure_total = mt;
+    }
+    auto t_begin = clk::now();
+    // step 1: create (upload)  — mkl_sparse_d_create_csr x2
+    g4s_csr_t A = nullptr, B = nullptr, C = nullptr;
+    int rc = g4s_csr_create_host(&A, M, K, arpt, acol, aval);
+    if (rc) return rc;
+    rc = g4s_csr_create_host(&B, K, N, brpt, bcol, bval);
+    if (rc) {
+        g4s_csr_destroy(A);
+        return rc;
+    }
+    auto t_create = clk::now();
+    // step 2: multiply (symbolic + numeric, sorted) — mkl_sparse_spmm + convert + order
+    rc = spgemm_run(A, B, &C, 0);
+    if (rc) {
+        g4s_csr_destroy(A);
+        g4s_csr_destroy(B);
+        return rc;
+    }
+    auto t_spmm = clk::now();
+    // step 3: export — callee-allocated host arrays, crpt[M] = cnnz
+    const long long cnnz = C->nnz;
+    int *crpt = (int *)alloc_index(sizeof(int) * ((size_t)M + 1), ctx);
+    int *ccol = (int *)alloc_index(sizeof(int) * (size_t)std::max<long long>(cnnz, 1), ctx);
+    double *cval = (double *)alloc_value(sizeof(double) * (size_t)std::max<long long>(cnnz, 1), ctx);
+    if (!crpt || !ccol || !cval) {
+        g4s_csr_destroy(A);
+        g4s_csr_destroy(B);
+        g4s_csr_destroy(C);
+        return fail(G4S_ERR_ALLOC, "g4s_mkl: output allocation failed");
+    }
+    rc = g4s_csr_download(C, crpt, ccol, cval);
+    auto t_export = clk::now();
+    g4s_csr_destroy(C);
+    g4s_csr_destroy(B);
+    g4s_csr_destroy(A);
+    auto t_destroy = clk::now();
+    if (rc) return rc;
+    *crpt_ = crpt;
+    *ccol_ = ccol;
+    *cval_ = cval;
+    *cnnz_ = (int)cnnz;
+    t->create = secs(t_begin, t_create);
+    t->spmm = secs(t_create, t_spmm);
+    t->convert = 0.0;
+    t->order = 0.0;
+    t->export_csr = secs(t_spmm, t_export);
+    t->destroy = secs(t_export, t_destroy);
+    t->total = secs(t_begin, t_destroy);
+    return G4S_OK;
+}
+
+int g4s_mkl(const int *arpt, const int *acol, const double *aval, const int *brpt, const int *bcol,
+            const double *bval, int **crpt_, int **ccol_, double **cval_, int M, int K, int N, int *cnnz_,
+            g4s_timings *timing) {
+    return g4s_mkl_alloc(arpt, acol, aval, brpt, bcol, bval, crpt_, ccol_, cval_, M, K, N, cnnz_, timing, nullptr,
+                         nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""GPU parity tests for SpGEMM C = A B (run on the B200 box: pytest -m gpu), through the C ABI.
+Bar (BASELINE.json north_star): row pointers, column indices and sparsity pattern bit-exact against the
+reference's HashSpGEMM<false,true> (via the pinned oracle and the committed golden vectors); fp64 values
+within 1e-12 relative, differences attributable to summation order: |c_gpu - c_ref| <= 1e-12 * (|A||B|)_ij."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from matrices import laplacian_2d, laplacian_3d_27, powerlaw_csr, random_csr, to_scipy, to_tuple, tridiag3
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def g4s():
+    import g4s_b200
+
+    assert g4s_b200.lib().g4s_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return g4s_b200
+
+
+def as_csr(g4s, t):
+    return g4s.CSR(t[0], t[1], t[2], t[3], t[4])
+
+
+def check_against(got, want_rpt, want_col, want_val, scale):
+    np.testing.assert_array_equal(got.rowptr, want_rpt)
+    np.testing.assert_array_equal(got.colids, want_col)
+    err = np.abs(got.values - want_val)
+    assert np.all(err <= RTOL * scale + 1e-300), "max err %g" % err.max()
+
+
+def oracle_product(oracle, A, B):
+    rpt, col, val = oracle.hash_spgemm(A, B)
+    Aabs = (A[0], A[1], A[2], A[3], np.abs(A[4]))
+    Babs = (B[0], B[1], B[2], B[3], np.abs(B[4]))
+    _, _, scale = oracle.hash_spgemm(Aabs, Babs)
+    return rpt, col, val, scale
+
+
+def banded(rows, half_width, seed):
+    """Every row has 2*half_width+1 entries: work per row of A*A up to (2h+1)^2 (classes 3-4)."""
+    rng = np.random.default_rng(seed)
+    diags = [rng.uniform(-1, 1, rows) for _ in range(2 * half_width + 1)]
+    return to_tuple(sp.diags(diags, list(range(-half_width, half_width + 1)), shape=(rows, rows)))
+
+
+CASES = {
+    "tridiag3": lambda: (tridiag3(),) * 2,                                             # class 1
+    "lap2d_64": lambda: (laplacian_2d(64),) * 2,                                       # class 1
+    "lap3d_8": lambda: (laplacian_3d_27(8),) * 2,                                      # class 2-3 (work up to 729)
+    "rand_rect": lambda: (random_csr(120, 200, 0.05, 2, empty_rows=True),
+                          random_csr(200, 90, 0.04, 3, empty_rows=True)),              # class 0-2
+    "rand_dense_rows": lambda: (random_csr(64, 64, 0.6, 4), random_csr(64, 64, 0.6, 5)),  # w capped by cols
+    "banded_20": lambda: (banded(600, 20, 6),) * 2,                                    # work 1681: class 3
+    "banded_35": lambda: (banded(5000, 35, 7),) * 2,                                   # work 5041, cols 5000: class 4
+    "powerlaw_hub": lambda: (powerlaw_csr(12000, 7, max_deg=6000),) * 2,               # class 5 (global tables)
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_spgemm_matches_oracle(g4s, oracle, name):
+    A, B = CASES[name]()
+    rpt, col, val, scale = oracle_product(oracle, A, B)
+    Ad, Bd = as_csr(g4s, A), as_csr(g4s, B)
+    C = g4s.HashSpGEMM(Ad, Bd).to_host()
+    assert (C.rows, C.cols) == (A[0], B[1])
+    check_against(C, rpt, col, val, scale)
+    total, _ = oracle.intprod(A[2], A[3], B[2])
+    assert g4s.compute_flop(Ad, Bd) == total
+    # the host-pointer mkl() twin gives the same CSR and fills the phase timings
+    t = g4s.Timings()
+    Ch = g4s.mkl(Ad, Bd, t)
+    check_against(Ch, rpt, col, val, scale)
+    assert t.total > 0 and abs(t.create + t.spmm + t.export_csr + t.destroy - t.total) < 1e-3
+    # reference-style comparison (CSR::operator==, EPSILON 1e-3)
+    assert C == g4s.CSR(A[0], B[1], rpt, col, val)
+
+
+def test_spgemm_golden_vectors(g4s):
+    """Outputs of the reference's own HashSpGEMM<false,true>, captured by tests/golden/make_golden.py."""
+    g = np.load(os.path.join(GOLDEN, "spgemm_golden.npz"))
+    for name in sorted({k.split("__")[0] for k in g.files}):
+        A = g4s.CSR(int(g[name + "__am"]), int(g[name + "__ak"]), g[name + "__arpt"], g[name + "__acol"], g[name + "__aval"])
+        B = g4s.CSR(int(g[name + "__ak"]), int(g[name + "__bn"]), g[name + "__brpt"], g[name + "__bcol"], g[name + "__bval"])
+        C = g4s.HashSpGEMM(A, B).to_host()
+        np.testing.assert_array_equal(C.rowptr, g[name + "__crpt"])
+        np.testing.assert_array_equal(C.colids, g[name + "__ccol"])
+        np.testing.assert_allclose(C.values, g[name + "__cval"], rtol=1e-12, atol=1e-13 * np.abs(g[name + "__cval"]).max())
+
+
+def test_spgemm_shape_errors(g4s):
+    A = as_csr(g4s, random_csr(10, 20, 0.2, 1))
+    with pytest.raises(ValueError):
+        g4s.HashSpGEMM(A, A)
+    Z = g4s.CSR(4, 4, np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    C = g4s.HashSpGEMM(Z, Z).to_host()
+    assert C.nnz == 0 and np.array_equal(C.rowptr, np.zeros(5, np.int32))
+
+
+def test_full_size_config4_properties(g4s):
+    """BASELINE config 4: A x A, 2-D 5-point Laplacian n = 2048 (4 194 304 rows) through the closed forms of
+    SURVEY.md §4: intprod = 25(n-2)^2+64(n-2)+36, nnz(A^2) = 13n^2-20n+4 = 54 484 996, sum(values) = 4n+8,
+    plus sortedness of every row and the interior stencil of A^2."""
+    import torch
+
+    n = 2048
+    A = g4s.CSR.laplacian2d(n)
+    assert A.nnz == 5 * n * n - 4 * n
+    assert g4s.compute_flop(A, A) == 25 * (n - 2) ** 2 + 64 * (n - 2) + 36 == 104783880
+    C = g4s.HashSpGEMM(A, A)
+    assert C.nnz == 13 * n * n - 20 * n + 4 == 54484996
+    Ch = C.to_host()
+    rowptr = torch.from_numpy(Ch.rowptr.astype(np.int64))
+    col = torch.from_numpy(Ch.colids.astype(np.int64))
+    val = torch.from_numpy(Ch.values)
+    assert float(val.sum()) == 4 * n + 8
+    # sorted, duplicate-free columns inside every row
+    inc = col[1:] > col[:-1]
+    row_start = torch.zeros(len(col), dtype=torch.bool)
+    row_start[rowptr[1:-1]] = True
+    assert bool(torch.all(inc | row_start[1:]))
+    # an interior row of A^2 is the 13-point biharmonic stencil: 20 at the centre, -8 x4, 2 x4, 1 x4
+    r = (n // 2) * n + n // 2
+    s, e = int(rowptr[r]), int(rowptr[r + 1])
+    assert e - s == 13
+    assert sorted(val[s:e].tolist()) == sorted([20.0] + [-8.0] * 4 + [2.0] * 4 + [1.0] * 4)
+    assert col[s:e].tolist() == [r - 2 * n, r - n - 1, r - n, r - n + 1, r - 2, r - 1, r, r + 1, r + 2,
+                                 r + n - 1, r + n, r + n + 1, r + 2 * n]
