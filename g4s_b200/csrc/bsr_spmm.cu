@@ -1,0 +1,183 @@
+// BSR SpMM for sm_100a (BASELINE config 5):  C[mb*bs, ncol] = A_bsr B,  bs x bs row-major blocks, row-major
+// dense B [kb*bs, ncol] and C.  The reference has no such routine (nearest relatives are
+// CitcomS's 3-dof node operator, citcoms/lib/Element_calculations.c:516-571); the oracle's restatement
+// (oracle/oracle_spmv.c: oracle_bsr_spmm) is the checker.
+//
+// Three kernels, one warp per block row:
+//   dmma   (bs = 3, ncol = 64): FP64 tensor cores, mma.sync.m8n8k4.f64 (DMMA.8x8x4 in SASS; tcgen05 has no FP64
+//          kind).  The product is taken transposed, C_I^T[64 x 3] = Bg^T[64 x 3nb] A_I^T[3nb x 3], so the dense
+//          64 columns fill the M = 8 side of eight tiles, the 3 block rows sit in N = 8 (3/8 used) and the
+//          blocks of the row are packed back to back along K (3nb, four at a time).
+//   fma    (bs = 3, ncol = 64): plain DFMA, each lane owns two columns of the 64 (128-bit loads of B).
+//   generic (any bs <= 8, any ncol): lane-per-column DFMA.
+// Which of dmma / fma is faster is a measured property of the part (profiles/): the default follows it.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace g4s {
+
+static int g_bsr_variant = 0;  // 0 auto, 1 fma, 2 dmma, 3 generic
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) bsr3_spmm64_dmma_kernel(int mb, const int *__restrict__ browptr,
+                                                               const int *__restrict__ bcolids,
+                                                               const double *__restrict__ bvalues,
+                                                               const double *__restrict__ B, double *__restrict__ C) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane & 3, q = lane >> 2;  // k: position along K inside a step; q: row of the A tile / col of the B tile
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+        const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        const int K = 3 * (p1 - p0);
+        double acc[8][2];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m][0] = acc[m][1] = 0.0;
+        for (int kk0 = 0; kk0 < K; kk0 += 4) {
+            const int kk = kk0 + k;
+            const bool valid = kk < K;
+            const int p = p0 + kk / 3, s = kk % 3;
+            double bfrag = 0.0;  // A_I^T[kk][q] = block p, entry (q, s)
+            const double *brow = B;
+            if (valid) {
+                const int J = __ldg(bcolids + p);
+                brow = B + ((size_t)J * 3 + s) * 64 + q;
+                if (q < 3) bfrag = __ldg(bvalues + (size_t)p * 9 + q * 3 + s);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double afrag = valid ? __ldg(brow + 8 * m) : 0.0;  // Bg^T[8m + q][kk]
+                dmma_m8n8k4(acc[m][0], acc[m][1], afrag, bfrag);
+            }
+        }
+        // D tile m: lane holds rows (dense column) 8m + q, cols (block row r) 2k and 2k+1
+        double *crow = C + (size_t)I * 3 * 64;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if (k == 0) {
+                crow[0 * 64 + 8 * m + q] = acc[m][0];
+                crow[1 * 64 + 8 * m + q] = acc[m][1];
+            } else if (k == 1) {
+                crow[2 * 64 + 8 * m + q] = acc[m][0];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bsr3_spmm64_fma_kernel(int mb, const int *__restrict__ browptr,
+                                                              const int *__restrict__ bcolids,
+                                                              const double *__restrict__ bvalues,
+                                                              const double *__restrict__ B, double *__restrict__ C) {
+    const int lane = threadIdx.x & 31;
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+        const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        double2 c0 = make_double2(0, 0), c1 = c0, c2 = c0;
+        for (int p = p0; p < p1; ++p) {
+            const int J = __ldg(bcolids + p);
+            const double *blk = bvalues + (size_t)p * 9;
+            const double2 *b = reinterpret_cast<const double2 *>(B + (size_t)J * 3 * 64) + lane;
+            const double2 b0 = __ldg(b), b1 = __ldg(b + 32), b2 = __ldg(b + 64);
+            const double a00 = __ldg(blk), a01 = __ldg(blk + 1), a02 = __ldg(blk + 2), a10 = __ldg(blk + 3),
+                         a11 = __ldg(blk + 4), a12 = __ldg(blk + 5), a20 = __ldg(blk + 6), a21 = __ldg(blk + 7),
+                         a22 = __ldg(blk + 8);
+            c0.x = fma(a00, b0.x, c0.x); c0.y = fma(a00, b0.y, c0.y);
+            c0.x = fma(a01, b1.x, c0.x); c0.y = fma(a01, b1.y, c0.y);
+            c0.x = fma(a02, b2.x, c0.x); c0.y = fma(a02, b2.y, c0.y);
+            c1.x = fma(a10, b0.x, c1.x); c1.y = fma(a10, b0.y, c1.y);
+            c1.x = fma(a11, b1.x, c1.x); c1.y = fma(a11, b1.y, c1.y);
+            c1.x = fma(a12, b2.x, c1.x); c1.y = fma(a12, b2.y, c1.y);
+            c2.x = fma(a20, b0.x, c2.x); c2.y = fma(a20, b0.y, c2.y);
+            c2.x = fma(a21, b1.x, c2.x); c2.y = fma(a21, b1.y, c2.y);
+            c2.x = fma(a22, b2.x, c2.x); c2.y = fma(a22, b2.y, c2.y);
+        }
+        double2 *c = reinterpret_cast<double2 *>(C + (size_t)I * 3 * 64) + lane;
+        c[0] = c0;
+        c[32] = c1;
+        c[64] = c2;
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) bsr_spmm_generic_kernel(int mb, const int *__restrict__ browptr,
+                                                               const int *__restrict__ bcolids,
+                                                               const double *__restrict__ bvalues, int ncol,
+                                                               const double *__restrict__ B, double *__restrict__ C) {
+    const int lane = threadIdx.x & 31;
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+        const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        for (int c = lane; c < ncol; c += 32) {
+            double acc[BS];
+#pragma unroll
+            for (int r = 0; r < BS; ++r) acc[r] = 0.0;
+            for (int p = p0; p < p1; ++p) {
+                const double *blk = bvalues + (size_t)p * BS * BS;
+                const double *b = B + (size_t)__ldg(bcolids + p) * BS * ncol + c;
+#pragma unroll
+                for (int s = 0; s < BS; ++s) {
+                    const double bv = __ldg(b + (size_t)s * ncol);
+#pragma unroll
+                    for (int r = 0; r < BS; ++r) acc[r] = fma(__ldg(blk + r * BS + s), bv, acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < BS; ++r) C[((size_t)I * BS + r) * ncol + c] = acc[r];
+        }
+    }
+}
+
+template <int BS>
+static void launch_generic(int grid, cudaStream_t st, int mb, const int *rp, const int *ci, const double *va, int ncol,
+                           const double *B, double *C) {
+    bsr_spmm_generic_kernel<BS><<<grid, 256, 0, st>>>(mb, rp, ci, va, ncol, B, C);
+}
+
+}  // namespace g4s
+
+using namespace g4s;
+
+extern "C" {
+
+int g4s_bsr_spmm_set_variant(int variant) {
+    if (variant < 0 || variant > 3) return fail(G4S_ERR_INVALID, "variant must be 0 (auto), 1 (fma), 2 (dmma) or 3 (generic)");
+    g_bsr_variant = variant;
+    return G4S_OK;
+}
+
+int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const int *bcolids_dev,
+                        const double *bvalues_dev, int ncol, const double *B_dev, double *C_dev, void *stream) {
+    if (mb < 0 || kb < 0 || bs < 1 || bs > 8 || ncol < 1 || !browptr_dev || !B_dev || !C_dev)
+        return fail(G4S_ERR_INVALID, "g4s_bsr_spmm_device: bad arguments (1 <= bs <= 8)");
+    if (mb == 0) return G4S_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<long long>(((long long)mb * 32 + 255) / 256, (long long)sm_count() * 16);
+    int variant = g_bsr_variant;
+    const bool fast_ok = bs == 3 && ncol == 64 && ((reinterpret_cast<uintptr_t>(B_dev) | reinterpret_cast<uintptr_t>(C_dev)) & 15) == 0;
+    if (variant == 0) variant = fast_ok ? 1 : 3;
+    if ((variant == 1 || variant == 2) && !fast_ok) variant = 3;
+    if (variant == 2) {
+        bsr3_spmm64_dmma_kernel<<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, C_dev);
+    } else if (variant == 1) {
+        bsr3_spmm64_fma_kernel<<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, C_dev);
+    } else {
+        switch (bs) {
+            case 1: launch_generic<1>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 2: launch_generic<2>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 3: launch_generic<3>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 4: launch_generic<4>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 5: launch_generic<5>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 6: launch_generic<6>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            case 7: launch_generic<7>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+            default: launch_generic<8>(grid, st, mb, browptr_dev, bcolids_dev, bvalues_dev, ncol, B_dev, C_dev); break;
+        }
+    }
+    G4S_CHECK_LAUNCH("bsr_spmm kernel");
+    return G4S_OK;
+}
+
+}  // extern "C"

@@ -206,6 +206,7 @@ int g4s_csr_destroy(g4s_csr_t h) {
         if (h->colids) cudaFree(h->colids);
         if (h->values) cudaFree(h->values);
     }
+    if (h->row_map) cudaFree(h->row_map);
     if (h->x_dev) cudaFree(h->x_dev);
     if (h->y_dev) cudaFree(h->y_dev);
     delete h;
@@ -249,6 +250,7 @@ int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const in
     if (!A || (!x_dev && A->cols) || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_device_ex: null argument");
     int rc = ensure_device();
     if (rc) return rc;
+    if (!row_map_dev) row_map_dev = A->row_map;  // a row-compressed handle scatters through its own map
     return spmv_run(A, x_dev, y_dev, row_map_dev, accumulate != 0, (cudaStream_t)stream);
 }
 

@@ -59,6 +59,10 @@ struct g4s_csr {
     double *values = nullptr;
     bool owns = false;
     g4s::SpmvPlan plan;
+    // row-compressed blocks (off-diagonal part of a multi-GPU row block): local row r is row row_map[r] of a
+    // block with full_rows rows
+    int *row_map = nullptr;
+    int full_rows = 0;
     // scratch for the host-pointer entry points
     double *x_dev = nullptr, *y_dev = nullptr;
 };

@@ -1,0 +1,192 @@
+// Host-side input formats of the mm/ path, behind the C ABI:
+//   g4s_csr_read_matrix_market  <- CSR<IT,NT>::construct            (mm/inc/CSR.h:485-669, banner :440-478)
+//   g4s_csr_from_edge_list      <- CSR<IT,NT>::CSR(graph&)           (mm/inc/CSR.h:255-329, graph.h:4-25)
+//   g4s_csr_submatrix           <- CSR(const CSR&, M_, N_, M_start, N_start) (mm/inc/CSR.h:691-733)
+// Same accepted inputs, same resulting CSR (row-major (row, col) order, duplicates KEPT by the MatrixMarket
+// reader and SUMMED by the edge-list constructor); malformed input returns G4S_ERR_FORMAT / G4S_ERR_IO where
+// the reference throws std::runtime_error.  Outputs are malloc'd (g4s_free).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "g4s_b200.h"
+
+namespace g4s {
+int fail(int status, const std::string &msg);
+}
+using g4s::fail;
+
+namespace {
+
+std::vector<std::string> words(const std::string &line) {
+    std::vector<std::string> out;
+    std::istringstream ss(line);
+    std::string w;
+    while (ss >> w) out.push_back(w);
+    return out;
+}
+
+template <class T>
+T *to_malloc(const std::vector<T> &v) {
+    T *p = static_cast<T *>(malloc(sizeof(T) * std::max<size_t>(v.size(), 1)));
+    if (p && !v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+struct Entry {
+    long key;  // cols * row + col
+    double val;
+};
+
+}  // namespace
+
+extern "C" {
+
+int g4s_csr_read_matrix_market(const char *path, int *rows, int *cols, int *nnz, int **rowptr, int **colids,
+                               double **values) {
+    if (!path || !rows || !cols || !nnz || !rowptr || !colids || !values)
+        return fail(G4S_ERR_INVALID, "g4s_csr_read_matrix_market: null argument");
+    std::ifstream in(path);
+    if (!in) return fail(G4S_ERR_IO, std::string("unable to open file \"") + path + "\" for reading");
+    std::string line;
+    std::getline(in, line);
+    const std::vector<std::string> banner = words(line);
+    if (banner.size() != 5 || banner[0] != "%%MatrixMarket" || banner[1] != "matrix")
+        return fail(G4S_ERR_FORMAT, "invalid MatrixMarket banner");
+    const std::string &storage = banner[2], &type = banner[3], &symmetry = banner[4];
+    if (storage != "array" && storage != "coordinate")
+        return fail(G4S_ERR_FORMAT, "invalid MatrixMarket storage format [" + storage + "]");
+    if (storage == "array") return fail(G4S_ERR_FORMAT, "not impl storage type array");
+    const bool pattern = type == "pattern", complex_ = type == "complex";
+    if (!pattern && !complex_ && type != "real" && type != "integer")
+        return fail(G4S_ERR_FORMAT, "invalid MatrixMarket data type [" + type + "]");
+    const bool general = symmetry == "general", skew = symmetry == "skew-symmetric";
+    if (!general && !skew && symmetry != "symmetric" && symmetry != "hermitian")
+        return fail(G4S_ERR_FORMAT, "invalid MatrixMarket symmetry [" + symmetry + "]");
+    if (symmetry == "hermitian") return fail(G4S_ERR_FORMAT, "not impl matrix type: hermitian");
+
+    do {
+        if (!std::getline(in, line)) line.clear();
+    } while (!line.empty() && line[0] == '%');
+    const std::vector<std::string> size = words(line);
+    if (size.size() != 3) return fail(G4S_ERR_FORMAT, "invalid MatrixMarket coordinate format");
+    const long R = atol(size[0].c_str()), C = atol(size[1].c_str()), E = atol(size[2].c_str());
+    if (R < 0 || C <= 0 || R > 2147483646L || C > 2147483647L)
+        return fail(G4S_ERR_FORMAT, "MatrixMarket dimensions out of int32 range");
+    if (E <= 0) return fail(G4S_ERR_FORMAT, "something wrong: nnz is 0");
+
+    std::vector<Entry> ent;
+    ent.reserve(general ? E : 2 * E);
+    long read = 0;
+    for (; read < E; ++read) {
+        long i, j;
+        double v = 1.0, imag;
+        if (!(in >> i >> j)) break;
+        if (!pattern && !(in >> v)) break;
+        if (complex_ && !(in >> imag)) break;
+        --i;
+        --j;
+        if (i < 0 || i >= R || j < 0 || j >= C) return fail(G4S_ERR_FORMAT, "MatrixMarket entry out of range");
+        ent.push_back({C * i + j, v});
+        if (!general && i != j) ent.push_back({C * j + i, skew ? -v : v});  // mirrored right after its source
+    }
+    if (read != E) return fail(G4S_ERR_FORMAT, "read nnz not equal to declared nnz " + std::to_string(read));
+    if (ent.size() > 2147483647UL) return fail(G4S_ERR_FORMAT, "more than 2^31-1 entries after symmetric expansion");
+    // (row, col) order.  The reference's std::sort leaves duplicates in unspecified order; file order is kept here.
+    std::stable_sort(ent.begin(), ent.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
+
+    std::vector<int> rp(R + 1, 0), ci(ent.size());
+    std::vector<double> va(ent.size());
+    for (size_t e = 0; e < ent.size(); ++e) {
+        rp[ent[e].key / C + 1]++;
+        ci[e] = static_cast<int>(ent[e].key % C);
+        va[e] = ent[e].val;
+    }
+    for (long r = 0; r < R; ++r) rp[r + 1] += rp[r];
+    *rows = static_cast<int>(R);
+    *cols = static_cast<int>(C);
+    *nnz = static_cast<int>(ent.size());
+    *rowptr = to_malloc(rp);
+    *colids = to_malloc(ci);
+    *values = to_malloc(va);
+    if (!*rowptr || !*colids || !*values) return fail(G4S_ERR_ALLOC, "g4s_csr_read_matrix_market: out of memory");
+    return G4S_OK;
+}
+
+int g4s_csr_from_edge_list(long m, long n, const long *start, const long *end, const double *w, int *nnz,
+                           int **rowptr, int **colids, double **values) {
+    if (m < 0 || n < 0 || (m > 0 && (!start || !end || !w)) || !nnz || !rowptr || !colids || !values)
+        return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: bad arguments");
+    if (n > 2147483646L) return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: more than 2^31-2 vertices");
+    for (long e = 0; e < m; ++e)
+        if (start[e] < 0 || start[e] >= n || end[e] < 0 || end[e] >= n)
+            return fail(G4S_ERR_FORMAT, "g4s_csr_from_edge_list: vertex id out of range");
+    // Runs of equal start vertex are sorted by (end, weight) and equal (start, end) pairs are summed left to
+    // right; a start vertex that shows up again later opens a new, unmerged run — as in the reference.
+    typedef std::pair<std::pair<long, long>, double> Edge;
+    std::vector<Edge> run, merged;
+    merged.reserve(static_cast<size_t>(m));
+    long e = 0;
+    while (e < m) {
+        run.clear();
+        const long s = start[e];
+        for (; e < m && start[e] == s; ++e) run.push_back(Edge(std::make_pair(s, end[e]), w[e]));
+        std::sort(run.begin(), run.end());
+        merged.push_back(run[0]);
+        for (size_t k = 1; k < run.size(); ++k) {
+            if (run[k].first == run[k - 1].first) merged.back().second += run[k].second;
+            else merged.push_back(run[k]);
+        }
+    }
+    if (merged.size() > 2147483647UL) return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: nnz exceeds int32");
+    std::vector<int> rp(n + 1, 0), ci(merged.size());
+    std::vector<double> va(merged.size());
+    for (const Edge &t : merged) rp[t.first.first + 1]++;
+    for (long r = 0; r < n; ++r) rp[r + 1] += rp[r];
+    std::vector<int> cursor(rp.begin(), rp.end() - 1);
+    for (const Edge &t : merged) {
+        const int pos = cursor[t.first.first]++;
+        ci[pos] = static_cast<int>(t.first.second);
+        va[pos] = t.second;
+    }
+    *nnz = static_cast<int>(merged.size());
+    *rowptr = to_malloc(rp);
+    *colids = to_malloc(ci);
+    *values = to_malloc(va);
+    if (!*rowptr || !*colids || !*values) return fail(G4S_ERR_ALLOC, "g4s_csr_from_edge_list: out of memory");
+    return G4S_OK;
+}
+
+int g4s_csr_submatrix(int rows, int cols, const int *rowptr, const int *colids, const double *values, int M_,
+                      int N_, int M_start, int N_start, int *nnz, int **orpt, int **ocol, double **oval) {
+    if (!rowptr || !nnz || !orpt || !ocol || !oval || M_ < 0 || N_ < 0 || M_start < 0 || N_start < 0)
+        return fail(G4S_ERR_INVALID, "g4s_csr_submatrix: bad arguments");
+    if ((long)M_ + M_start > rows) return fail(G4S_ERR_SHAPE, "matrix subsect error M");
+    if ((long)N_ + N_start > cols) return fail(G4S_ERR_SHAPE, "matrix subsect error N");
+    std::vector<int> rp(M_ + 1, 0), ci;
+    std::vector<double> va;
+    for (int i = 0; i < M_; ++i) {
+        for (int j = rowptr[i + M_start]; j < rowptr[i + M_start + 1]; ++j) {
+            const int c = colids[j];
+            if (c >= N_start && c < N_start + N_) {
+                ci.push_back(c - N_start);
+                va.push_back(values[j]);
+            }
+        }
+        rp[i + 1] = static_cast<int>(ci.size());
+    }
+    *nnz = static_cast<int>(ci.size());
+    *orpt = to_malloc(rp);
+    *ocol = to_malloc(ci);
+    *oval = to_malloc(va);
+    if (!*orpt || !*ocol || !*oval) return fail(G4S_ERR_ALLOC, "g4s_csr_submatrix: out of memory");
+    return G4S_OK;
+}
+
+}  // extern "C"

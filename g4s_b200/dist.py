@@ -1,0 +1,271 @@
+"""Row-partitioned multi-GPU SpMV / SpGEMM: one process per GPU, torch.distributed (NCCL over NVLink) for the
+exchange, libg4s_b200.so for every kernel.
+
+SpMV: rows are cut by nnz balance (BIN::set_rows_offset's cut, mm/inc/BIN.h:100-122, applied to the
+nnz prefix = rowptr); rank r owns rows/x/y entries [cuts[r], cuts[r+1]).  Its row block is split once into the
+DIAGONAL block (columns it owns) and the row-compressed OFF-DIAGONAL block.  Every product then runs
+
+    comm stream : pack the x entries other ranks need  ->  all_to_all (NCCL)  ->  halo buffer
+    main stream : y  = A_diag x_local                      (overlaps the exchange)
+                  y += A_off  halo                         (after the exchange event)
+
+"halo" mode moves only the x entries that are referenced (for a stencil: two planes per neighbour instead of the
+whole vector); "allgather" mode is the plain NCCL all-gather of x named in BASELINE.json's north_star and is the
+fallback for matrices whose off-diagonal block references most of x (R-MAT).
+
+SpGEMM: A is cut by intermediate-product balance, B is replicated with NCCL broadcast, each rank multiplies its
+row block; C stays distributed (global row pointers = local ones + an exclusive scan of per-rank nnz).
+
+The exchange plan is backend-agnostic: `ops` supplies the local kernels (GpuOps = the CUDA library; the CPU
+tests plug in an oracle-backed stand-in so the plan runs under gloo with world_size 2)."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import check, f64p, i32p, lib
+from .csr import CSR, HashSpGEMM, _stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------ partitioning
+def partition_by_prefix(prefix_fn, rows, parts):
+    """cuts[p+1] = lower_bound(prefix, ceil(total/parts)*(p+1)) over prefix[0..rows], last cut = rows — the rule of
+    BIN::set_rows_offset (and of g4s_partition_rows_*), for a prefix given as a function (closed-form generators)."""
+    total = prefix_fn(rows)
+    avg = (total + parts - 1) // parts
+    cuts = [0]
+    for p in range(parts):
+        target = avg * (p + 1)
+        lo, hi = 0, rows + 1
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if prefix_fn(mid) < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        cuts.append(min(lo, rows))
+    cuts[-1] = rows
+    return cuts
+
+
+def partition_rows(prefix, parts):
+    """Same cut on an explicit prefix array (rowptr for nnz balance); calls the C ABI partitioner."""
+    prefix = np.ascontiguousarray(prefix, dtype=np.int64)
+    cuts = np.zeros(parts + 1, dtype=np.int32)
+    check(lib().g4s_partition_rows_i64(prefix.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int(len(prefix) - 1),
+                                       C.c_int(parts), cuts.ctypes.data_as(i32p)))
+    return [int(c) for c in cuts]
+
+
+# ------------------------------------------------------------------------------------------------ local kernels
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class GpuOps:
+    """Local operations on the GPU through the C ABI."""
+    device_type = "cuda"
+
+    def __init__(self):
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def split(self, A, c0, c1):
+        d, o = C.c_void_p(), C.c_void_p()
+        check(lib().g4s_csr_split_columns(A.handle, C.c_int(c0), C.c_int(c1), C.byref(d), C.byref(o), C.c_void_p(0)))
+        return CSR._from_handle(d), CSR._from_handle(o)
+
+    def compact(self, off):
+        ptr, n = i32p(), C.c_int()
+        check(lib().g4s_csr_compact_columns(off.handle, C.byref(ptr), C.byref(n), C.c_void_p(0)))
+        addr = C.cast(ptr, C.c_void_p).value
+        if n.value:
+            t = torch.as_tensor(_DevArray(addr, n.value, "<i4"), device=self.device).clone()
+        else:
+            t = torch.empty(0, dtype=torch.int32, device=self.device)
+        check(lib().g4s_device_free(C.c_void_p(addr)))
+        off.cols = n.value
+        return t
+
+    def colids_view(self, A):
+        """Zero-copy torch view of a handle's column ids (used to remap them for the all-gather layout)."""
+        _, ci, _ = A.device_arrays()
+        return torch.as_tensor(_DevArray(ci, A.nnz, "<i4"), device=self.device) if A.nnz else \
+            torch.empty(0, dtype=torch.int32, device=self.device)
+
+    def gather(self, dst, src, idx, stream):
+        check(lib().g4s_gather_f64(C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                   C.c_longlong(idx.numel()), _stream_ptr(stream)))
+
+    def spmv(self, A, x, y, stream, accumulate=False):
+        if A.rows == 0:
+            return
+        if accumulate:
+            A.spmv_device(x.data_ptr(), y.data_ptr(), stream=stream, accumulate=True)
+        else:
+            A.spmv_device(x.data_ptr(), y.data_ptr(), stream=stream)
+
+
+# ------------------------------------------------------------------------------------------------ SpMV
+class DistSpMV:
+    """y = A x with A row-partitioned over the ranks of `group`.
+
+    A_local : CSR holding this rank's rows [cuts[rank], cuts[rank+1]) with GLOBAL column ids (cols = global n).
+    cuts    : world+1 row cuts (also the ownership of x and y entries; A must be square)."""
+
+    def __init__(self, A_local, cuts, group=None, mode="auto", ops=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.ops = ops if ops is not None else GpuOps()
+        self.cuts = [int(c) for c in cuts]
+        assert len(self.cuts) == self.world + 1
+        self.c0, self.c1 = self.cuts[self.rank], self.cuts[self.rank + 1]
+        self.local_rows = self.c1 - self.c0
+        assert A_local.rows == self.local_rows, "A_local must hold exactly this rank's rows"
+        dev = self.ops.device
+        self.diag, self.off = self.ops.split(A_local, self.c0, self.c1)
+        # how much of x the off-diagonal block references decides the exchange
+        needed = self.ops.compact(self.off)
+        frac = torch.tensor([needed.numel() / max(1, self.cuts[-1] - self.local_rows)], dtype=torch.float64, device=dev)
+        dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=self.group)
+        self.mode = mode if mode != "auto" else ("allgather" if float(frac.item()) > 0.5 else "halo")
+        bounds = torch.tensor(self.cuts, dtype=needed.dtype, device=dev)
+        # needed is sorted, hence grouped by owner
+        edges = torch.searchsorted(needed, bounds)
+        self.recv_counts = [int(v) for v in (edges[1:] - edges[:-1]).tolist()]
+        self.n_halo = int(needed.numel())
+        if self.mode == "halo":
+            mine = torch.tensor(self.recv_counts, dtype=torch.int64, device=dev)
+            theirs = torch.empty_like(mine)
+            dist.all_to_all_single(theirs, mine, group=self.group)
+            self.send_counts = [int(v) for v in theirs.tolist()]
+            req_in = torch.empty(sum(self.send_counts), dtype=needed.dtype, device=dev)
+            dist.all_to_all_single(req_in, needed, self.send_counts, self.recv_counts, group=self.group)
+            self.send_idx = (req_in - self.c0).to(torch.int32).contiguous()
+            self.send_buf = torch.empty(self.send_idx.numel(), dtype=torch.float64, device=dev)
+            self.halo = torch.empty(max(self.n_halo, 1), dtype=torch.float64, device=dev)
+            self.exchange_bytes = 8 * self.n_halo
+        else:
+            # all-gather layout: slice q sits at q*slot; off-diagonal column ids (halo positions after compact)
+            # are mapped to that layout once
+            self.slot = max(self.cuts[q + 1] - self.cuts[q] for q in range(self.world))
+            owner = torch.searchsorted(bounds, needed, right=True) - 1
+            padded = (owner * self.slot + (needed - bounds[owner])).to(torch.int32)
+            col = self.ops.colids_view(self.off)
+            if col.numel():
+                col.copy_(padded[col.long()])
+            self.off.cols = self.slot * self.world
+            self.x_pad = torch.zeros(self.slot, dtype=torch.float64, device=dev)
+            self.halo = torch.empty(self.slot * self.world, dtype=torch.float64, device=dev)
+            self.exchange_bytes = 8 * self.slot * (self.world - 1)
+        self.comm_stream = torch.cuda.Stream() if self.ops.device_type == "cuda" else None
+        self.launches_per_step = 1 + (1 if self.off.rows else 0) + (1 if self.mode == "halo" and self.send_idx.numel() else 0)
+
+    # -- convenience constructors ----------------------------------------------------------------------------
+    @classmethod
+    def laplacian3d27(cls, n, group=None, mode="auto"):
+        """BASELINE configs[1]: each rank generates its own nnz-balanced row block on its GPU."""
+        group = group if group is not None else dist.group.WORLD
+        L = lib()
+        rows = n ** 3
+        cuts = partition_by_prefix(lambda r: int(L.g4s_laplacian3d27_nnz(C.c_int(n), C.c_longlong(0), C.c_longlong(r))),
+                                   rows, dist.get_world_size(group))
+        r = dist.get_rank(group)
+        A_local = CSR.laplacian3d27(n, cuts[r], cuts[r + 1])
+        op = cls(A_local, cuts, group, mode)
+        A_local.make_empty()  # the split blocks are what the product uses
+        return op
+
+    @classmethod
+    def from_global(cls, A, group=None, mode="auto", ops=None):
+        """Every rank holds the same host CSR `A` (square); it keeps the rows of its nnz-balanced cut."""
+        group = group if group is not None else dist.group.WORLD
+        A = A.to_host()
+        world, r = dist.get_world_size(group), dist.get_rank(group)
+        cuts = partition_rows(A.rowptr, world)
+        s, e = int(A.rowptr[cuts[r]]), int(A.rowptr[cuts[r + 1]])
+        local = CSR(cuts[r + 1] - cuts[r], A.cols, A.rowptr[cuts[r]:cuts[r + 1] + 1] - s, A.colids[s:e], A.values[s:e])
+        return cls(local, cuts, group, mode, ops)
+
+    # -- the product ---------------------------------------------------------------------------------------------
+    def apply(self, x_local, y_local):
+        """y_local = (A x)[owned rows]; x_local / y_local are this rank's slices (device tensors, float64)."""
+        ops = self.ops
+        if ops.device_type != "cuda":
+            return self._apply_sync(x_local, y_local)
+        main = torch.cuda.current_stream()
+        comm = self.comm_stream
+        comm.wait_stream(main)  # x_local is ready on the main stream
+        with torch.cuda.stream(comm):
+            self._exchange(x_local, comm)
+            done = comm.record_event()
+        ops.spmv(self.diag, x_local, y_local, main)            # overlaps the exchange
+        main.wait_event(done)
+        ops.spmv(self.off, self.halo, y_local, main, accumulate=True)
+        return y_local
+
+    def _exchange(self, x_local, stream):
+        if self.mode == "halo":
+            if self.send_idx.numel():
+                self.ops.gather(self.send_buf, x_local, self.send_idx, stream)
+            dist.all_to_all_single(self.halo[:self.n_halo], self.send_buf, self.recv_counts, self.send_counts,
+                                   group=self.group)
+        else:
+            self.x_pad[:self.local_rows].copy_(x_local)
+            dist.all_gather_into_tensor(self.halo, self.x_pad, group=self.group)
+
+    def _apply_sync(self, x_local, y_local):
+        self._exchange(x_local, None)
+        self.ops.spmv(self.diag, x_local, y_local, None)
+        self.ops.spmv(self.off, self.halo, y_local, None, accumulate=True)
+        return y_local
+
+
+# ------------------------------------------------------------------------------------------------ SpGEMM
+class DistSpGEMM:
+    """C = A B with A's rows cut by intermediate-product balance and B replicated by NCCL broadcast from rank 0.
+
+    `A_local` holds this rank's rows of A; `B` is the full matrix on rank 0 (None elsewhere)."""
+
+    def __init__(self, A_local, B, cuts, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.cuts = [int(c) for c in cuts]
+        self.A_local = A_local
+        dev = torch.device("cuda", torch.cuda.current_device())
+        meta = torch.zeros(3, dtype=torch.int64, device=dev)
+        if self.rank == 0:
+            meta[0], meta[1], meta[2] = B.rows, B.cols, B.nnz
+        dist.broadcast(meta, 0, group=self.group)
+        rows, cols, nnz = (int(v) for v in meta.tolist())
+        if self.rank == 0:
+            rp, ci, va = B.device_arrays()
+            self._b = (torch.as_tensor(_DevArray(rp, rows + 1, "<i4"), device=dev),
+                       torch.as_tensor(_DevArray(ci, nnz, "<i4"), device=dev),
+                       torch.as_tensor(_DevArray(va, nnz, "<f8"), device=dev))
+            self.B = B
+        else:
+            self._b = (torch.empty(rows + 1, dtype=torch.int32, device=dev),
+                       torch.empty(nnz, dtype=torch.int32, device=dev),
+                       torch.empty(nnz, dtype=torch.float64, device=dev))
+        for t in self._b:
+            dist.broadcast(t, 0, group=self.group)
+        self.broadcast_bytes = 4 * (rows + 1) + 12 * nnz
+        if self.rank != 0:
+            h = C.c_void_p()
+            check(lib().g4s_csr_create_device(C.byref(h), C.c_int(rows), C.c_int(cols), C.c_void_p(self._b[0].data_ptr()),
+                                              C.c_void_p(self._b[1].data_ptr()), C.c_void_p(self._b[2].data_ptr()),
+                                              C.c_void_p(0)))
+            self.B = CSR._from_handle(h)
+
+    def multiply(self):
+        """Returns (C_local, global_nnz_offset): this rank's rows of C and where they start in the global CSR."""
+        C_local = HashSpGEMM(self.A_local, self.B)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mine = torch.tensor([C_local.nnz], dtype=torch.int64, device=dev)
+        every = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        offset = int(every[:self.rank].sum().item())
+        self.global_nnz = int(every.sum().item())
+        return C_local, offset

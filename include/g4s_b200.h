@@ -158,6 +158,19 @@ long long compute_flop_host(const int *arpt, const int *acol, const int *brpt, i
 int g4s_partition_rows_i32(const int *work_prefix, int rows, int parts, int *cuts /* parts+1 */);
 int g4s_partition_rows_i64(const long long *work_prefix, int rows, int parts, int *cuts);
 
+/* Multi-GPU building blocks.  A GPU's row block A[r0:r1, :] (global column ids) is split into
+ * the DIAGONAL block (columns [c0,c1) it owns, rebased to 0) and the OFF-DIAGONAL block (every other column),
+ * which is row-compressed: only rows holding an off-diagonal entry are kept; g4s_csr_row_map gives the map back to
+ * local rows and g4s_spmv_device_ex on that handle scatters through it.  g4s_csr_compact_columns returns the
+ * sorted distinct columns a block references (the x entries to fetch from other GPUs; release with
+ * g4s_device_free) and rewrites the block's column ids to positions in that list.  g4s_gather_f64 packs
+ * dst[k] = src[idx[k]].  The exchange itself (NCCL) is the caller's, see g4s_b200/dist.py. */
+int g4s_csr_split_columns(g4s_csr_t A, int c0, int c1, g4s_csr_t *diag, g4s_csr_t *off, void *stream);
+int g4s_csr_row_map(g4s_csr_t h, const int **row_map_dev, int *full_rows);
+int g4s_csr_compact_columns(g4s_csr_t A, int **needed_cols_dev, int *n_needed, void *stream);
+int g4s_gather_f64(double *dst_dev, const double *src_dev, const int *idx_dev, long long n, void *stream);
+int g4s_device_free(void *p);
+
 /* ------------------------------------------------------------------------------------------------------
  * Loaders (host) — CSR::construct (mm/inc/CSR.h:485-669) and CSR(graph&) (mm/inc/CSR.h:255-329).
  * Outputs are malloc'd (g4s_free).
@@ -183,6 +196,13 @@ int g4s_csr_generate_laplacian3d27(g4s_csr_t *out, int n, long long row0, long l
 /* Graph500 R-MAT (a,b,c,d = .57,.19,.19,.05), 2^scale vertices, edge_factor * 2^scale generated edges,
  * weights U(0,1), duplicates summed (CSR(graph&) semantics); counter-based generator keyed by `seed`. */
 int g4s_csr_generate_rmat(g4s_csr_t *out, int scale, int edge_factor, unsigned long long seed, void *stream);
+/* the edge list alone, laid out as class graph (long start[m], end[m]; double w[m]) in device memory */
+int g4s_rmat_edges_device(int scale, long long m, unsigned long long seed, long *start_dev, long *end_dev,
+                          double *w_dev, void *stream);
+/* Device graph-to-CSR loader: CSR(graph&) (mm/inc/CSR.h:255-329) for an edge list already on the GPU.  Edges are
+ * ordered by (start, end) and equal pairs summed; the input need not be grouped by start vertex. */
+int g4s_csr_from_edges_device(long m, long n, const long *start_dev, const long *end_dev, const double *w_dev,
+                              g4s_csr_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * BSR SpMM (BASELINE config 5): C[mb*bs, ncol] = A_bsr B, bs x bs row-major blocks, row-major dense B, C.
@@ -190,6 +210,8 @@ int g4s_csr_generate_rmat(g4s_csr_t *out, int scale, int edge_factor, unsigned l
  * ---------------------------------------------------------------------------------------------------- */
 int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const int *bcolids_dev,
                         const double *bvalues_dev, int ncol, const double *B_dev, double *C_dev, void *stream);
+/* kernel choice for bs = 3, ncol = 64: 0 automatic, 1 DFMA, 2 DMMA (FP64 tensor cores), 3 generic */
+int g4s_bsr_spmm_set_variant(int variant);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,199 @@
+"""GPU parity tests (pytest -m gpu) for the rest of the C ABI: the reference-named dense mv entry points
+(mv/mv.c:6-27), the device graph-to-CSR loader and R-MAT generator, the BSR SpMM kernels, and the multi-GPU
+building blocks (column split, halo compaction, gather)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from matrices import laplacian_3d_27, powerlaw_csr, random_csr, to_scipy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g4s():
+    import g4s_b200
+
+    assert g4s_b200.lib().g4s_device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return g4s_b200
+
+
+# ---------------------------------------------------------------- dense mv (mv/mv.c:6-27) ----------------------
+@pytest.mark.parametrize("dim", [1, 7, 64, 257, 1500])
+def test_dense_mv_entry_points_match_oracle(g4s, oracle, dim):
+    rng = np.random.default_rng(dim)
+    A = rng.uniform(-1, 1, (dim, dim))
+    B = rng.uniform(-1, 1, dim)
+    absA, absB = np.abs(A), np.abs(B)
+    tol = 1e-12 * (absA.sum(axis=0).max() + absA.sum(axis=1).max()) * max(absB.max(), 1e-300)
+    for name, oname in (("dgemv", "dgemv"), ("dsymv", "dsymv"), ("dtrmv", "dtrmv"), ("sspmv", "dspmv")):
+        Bo, Co = oracle.dense_mv(oname, A, B)
+        Ag, Bg, Cg = A.copy().reshape(-1), B.copy(), np.full(dim, 123.0)
+        getattr(g4s.mv, "matrix_multiply_" + name)(Ag, Bg, Cg, dim)
+        if name == "dtrmv":  # in place on B, C untouched (mv/mv.c:12-15)
+            np.testing.assert_allclose(Bg, Bo, rtol=0, atol=tol)
+            np.testing.assert_array_equal(Cg, 123.0)
+        else:
+            np.testing.assert_allclose(Cg, Co, rtol=0, atol=tol)
+            np.testing.assert_array_equal(Bg, B)
+        np.testing.assert_array_equal(Ag, A.reshape(-1))
+
+
+def test_dense_mv_equals_sparse_path(g4s):
+    """dgemv on the row-major-filled dense buffer is y = M^T x; the CSR SpMV of M^T agrees."""
+    M = random_csr(300, 300, 0.05, 9)
+    dense = to_scipy(M).toarray()
+    x = np.random.default_rng(2).uniform(-1, 1, 300)
+    Cg = np.zeros(300)
+    g4s.mv.matrix_multiply_dgemv(dense.copy().reshape(-1), x.copy(), Cg, 300)
+    Mt = to_scipy(M).T.tocsr()
+    Mt.sort_indices()
+    y = g4s.CSR(300, 300, Mt.indptr, Mt.indices, Mt.data).spmv(x)
+    np.testing.assert_allclose(Cg, y, rtol=0, atol=1e-12 * 300)
+
+
+# ---------------------------------------------------------------- graph -> CSR loader, R-MAT ----------------------
+def test_device_edge_list_loader_matches_oracle(g4s, oracle):
+    import torch
+
+    rng = np.random.default_rng(23)
+    n, m = 1000, 40000
+    start, end, w = rng.integers(0, n, m), rng.integers(0, n, m), rng.uniform(0, 1, m)
+    order = np.argsort(start, kind="stable")  # the reference wants edges grouped by start vertex
+    want = oracle.csr_from_graph(n, start[order], end[order], w[order])
+    sd, ed, wd = (torch.from_numpy(a).cuda() for a in (start.astype(np.int64), end.astype(np.int64), w))
+    h = C.c_void_p()
+    g4s._lib.check(g4s.lib().g4s_csr_from_edges_device(C.c_long(m), C.c_long(n), C.c_void_p(sd.data_ptr()),
+                                                      C.c_void_p(ed.data_ptr()), C.c_void_p(wd.data_ptr()),
+                                                      C.byref(h), C.c_void_p(0)))
+    got = g4s.CSR._from_handle(h).to_host()
+    np.testing.assert_array_equal(got.rowptr, want[2])
+    np.testing.assert_array_equal(got.colids, want[3])
+    np.testing.assert_allclose(got.values, want[4], rtol=1e-12, atol=0)  # duplicates summed in another order
+    assert got.nnz < m
+
+
+def test_rmat_generator(g4s):
+    import torch
+
+    scale, ef = 12, 16
+    A = g4s.CSR.rmat(scale, ef, seed=20240601).to_host()
+    n = 1 << scale
+    assert (A.rows, A.cols) == (n, n) and 0 < A.nnz <= ef * n
+    assert np.all(np.diff(A.rowptr) >= 0) and A.rowptr[-1] == A.nnz
+    for r in (0, 1, n // 2):
+        seg = A.colids[A.rowptr[r]:A.rowptr[r + 1]]
+        assert np.all(np.diff(seg) > 0)  # sorted, duplicates merged
+    deg = np.diff(A.rowptr)
+    assert deg.max() > 20 * deg.mean() and (deg == 0).sum() > n // 20  # power-law: hubs and empty rows
+    # the merged weights add up to the sum of all generated weights; regeneration is reproducible
+    m = ef * n
+    sd, ed = (torch.empty(m, dtype=torch.int64, device="cuda") for _ in range(2))
+    wd = torch.empty(m, dtype=torch.float64, device="cuda")
+    g4s._lib.check(g4s.lib().g4s_rmat_edges_device(C.c_int(scale), C.c_longlong(m), C.c_ulonglong(20240601),
+                                                  C.c_void_p(sd.data_ptr()), C.c_void_p(ed.data_ptr()),
+                                                  C.c_void_p(wd.data_ptr()), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert abs(float(wd.sum()) - A.values.sum()) <= 1e-9 * m
+    assert 0.0 <= float(wd.min()) and float(wd.max()) < 1.0
+    dense_count = torch.unique(sd * n + ed).numel()
+    assert dense_count == A.nnz
+    B = g4s.CSR.rmat(scale, ef, seed=20240601).to_host()
+    assert np.array_equal(A.colids, B.colids) and np.array_equal(A.values, B.values)
+    # quadrant probabilities: the top-left quadrant gets ~57 % of the edges
+    frac = float(((sd < n // 2) & (ed < n // 2)).double().mean())
+    assert abs(frac - 0.57) < 0.02
+
+
+def test_spmv_on_rmat_matches_oracle(g4s, oracle):
+    A = g4s.CSR.rmat(14, 16, seed=7).to_host()
+    x = np.random.default_rng(4).uniform(-1, 1, A.cols)
+    y = A.spmv(x)
+    want = oracle.spmv_csr(A.rowptr, A.colids, A.values, x)
+    scale = oracle.spmv_csr_abs(A.rowptr, A.colids, A.values, x)
+    assert np.all(np.abs(y - want) <= 1e-12 * scale + 1e-300)
+
+
+# ---------------------------------------------------------------- BSR SpMM ------------------------------------------
+def bsr_case(mb, density, bs, seed):
+    rng = np.random.default_rng(seed)
+    pat = (sp.random(mb, mb, density=density, random_state=rng, format="csr") + sp.identity(mb, format="csr")).tocsr()
+    pat.sort_indices()
+    blocks = rng.uniform(-1, 1, (pat.nnz, bs, bs))
+    return pat.indptr.astype(np.int32), pat.indices.astype(np.int32), blocks
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_bsr3_spmm64_matches_oracle(g4s, oracle, variant):
+    import torch
+
+    mb, bs, ncol = 500, 3, 64
+    rp, ci, blocks = bsr_case(mb, 0.03, bs, 5)
+    Bd = np.random.default_rng(777).uniform(-1, 1, (mb * bs, ncol))
+    want = oracle.bsr_spmm(rp, ci, blocks.reshape(-1), bs, Bd)
+    absw = oracle.bsr_spmm(rp, ci, np.abs(blocks).reshape(-1), bs, np.abs(Bd))
+    t = [torch.from_numpy(a).cuda() for a in (rp, ci, blocks.reshape(-1), Bd.reshape(-1))]
+    out = torch.full((mb * bs * ncol,), -7.0, dtype=torch.float64, device="cuda")
+    L = g4s.lib()
+    g4s._lib.check(L.g4s_bsr_spmm_set_variant(C.c_int(variant)))
+    g4s._lib.check(L.g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(bs), C.c_void_p(t[0].data_ptr()),
+                                         C.c_void_p(t[1].data_ptr()), C.c_void_p(t[2].data_ptr()), C.c_int(ncol),
+                                         C.c_void_p(t[3].data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    L.g4s_bsr_spmm_set_variant(C.c_int(0))
+    got = out.cpu().numpy().reshape(mb * bs, ncol)
+    assert np.all(np.abs(got - want) <= 1e-12 * absw + 1e-300)
+
+
+@pytest.mark.parametrize("bs,ncol", [(1, 5), (2, 33), (4, 64), (8, 7)])
+def test_bsr_generic_shapes(g4s, oracle, bs, ncol):
+    import torch
+
+    mb = 120
+    rp, ci, blocks = bsr_case(mb, 0.05, bs, bs)
+    Bd = np.random.default_rng(1).uniform(-1, 1, (mb * bs, ncol))
+    want = oracle.bsr_spmm(rp, ci, blocks.reshape(-1), bs, Bd)
+    t = [torch.from_numpy(a).cuda() for a in (rp, ci, blocks.reshape(-1), Bd.reshape(-1))]
+    out = torch.empty(mb * bs * ncol, dtype=torch.float64, device="cuda")
+    g4s._lib.check(g4s.lib().g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(bs), C.c_void_p(t[0].data_ptr()),
+                                                C.c_void_p(t[1].data_ptr()), C.c_void_p(t[2].data_ptr()),
+                                                C.c_int(ncol), C.c_void_p(t[3].data_ptr()),
+                                                C.c_void_p(out.data_ptr()), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy().reshape(mb * bs, ncol), want, rtol=0, atol=1e-11)
+
+
+# ---------------------------------------------------------------- multi-GPU building blocks on one GPU -------------
+def test_split_compact_gather_reassemble(g4s, oracle):
+    """y = A_diag x_own + A_off x_halo reproduces the whole product for every rank's block (emulated on one GPU)."""
+    import torch
+
+    from g4s_b200.dist import GpuOps, partition_rows
+
+    ops = GpuOps()
+    for A in (laplacian_3d_27(10), powerlaw_csr(4000, 13, max_deg=900)):
+        x = np.random.default_rng(8).uniform(-1, 1, A[1])
+        want = oracle.spmv_csr(A[2], A[3], A[4], x)
+        scale = oracle.spmv_csr_abs(A[2], A[3], A[4], x)
+        xd = torch.from_numpy(x).cuda()
+        cuts = partition_rows(A[2], 3)
+        for r in range(3):
+            c0, c1 = cuts[r], cuts[r + 1]
+            s, e = int(A[2][c0]), int(A[2][c1])
+            local = g4s.CSR(c1 - c0, A[1], A[2][c0:c1 + 1] - s, A[3][s:e], A[4][s:e])
+            diag, off = ops.split(local, c0, c1)
+            assert diag.nnz + off.nnz == e - s and diag.cols == c1 - c0
+            needed = ops.compact(off)
+            nh = needed.cpu().numpy()
+            assert np.all(np.diff(nh) > 0) and not np.any((nh >= c0) & (nh < c1))
+            halo = torch.empty(max(len(nh), 1), dtype=torch.float64, device="cuda")
+            if len(nh):
+                ops.gather(halo[:len(nh)], xd, needed, None)
+            y = torch.full((c1 - c0,), 9.0, dtype=torch.float64, device="cuda")
+            ops.spmv(diag, xd[c0:c1].contiguous(), y, None)
+            ops.spmv(off, halo, y, None, accumulate=True)
+            torch.cuda.synchronize()
+            err = np.abs(y.cpu().numpy() - want[c0:c1])
+            assert np.all(err <= 1e-12 * scale[c0:c1] + 1e-300)
