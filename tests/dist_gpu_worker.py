@@ -1,0 +1,84 @@
+"""Worker for tests/test_dist_gpu.py (launched with torchrun, one rank per GPU, NCCL)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from matrices import laplacian_2d, laplacian_3d_27, powerlaw_csr
+    from oracle.binding import Oracle
+
+    import g4s_b200
+    from g4s_b200.dist import DistSpGEMM, DistSpMV, partition_rows
+
+    oracle = Oracle()
+    ok = True
+    # ---- SpMV, both exchange modes ---------------------------------------------------------------------------
+    for name, A in (("lap3d", laplacian_3d_27(14)), ("powerlaw", powerlaw_csr(6000, 3, max_deg=900))):
+        x = np.random.default_rng(7).uniform(-1, 1, A[1])
+        want = oracle.spmv_csr(A[2], A[3], A[4], x)
+        scale = oracle.spmv_csr_abs(A[2], A[3], A[4], x)
+        for mode in ("halo", "allgather", "auto"):
+            op = DistSpMV.from_global(g4s_b200.CSR(A[0], A[1], A[2], A[3], A[4]), mode=mode)
+            xl = torch.from_numpy(x[op.c0:op.c1].copy()).cuda()
+            yl = torch.zeros(op.local_rows, dtype=torch.float64, device="cuda")
+            for _ in range(3):  # repeated application reuses the plan and the streams
+                op.apply(xl, yl)
+            torch.cuda.synchronize()
+            err = np.abs(yl.cpu().numpy() - want[op.c0:op.c1])
+            good = bool(np.all(err <= 1e-12 * scale[op.c0:op.c1] + 1e-300))
+            if not good:
+                print("rank %d: spmv %s/%s max err %g" % (rank, name, mode, err.max()), flush=True)
+            ok = ok and good
+    # device-generated row blocks (the bench path)
+    n = 24
+    op = DistSpMV.laplacian3d27(n)
+    A = oracle.gen_laplacian3d27(n)
+    x = np.random.default_rng(9).uniform(-1, 1, A[1])
+    want = oracle.spmv_csr(A[2], A[3], A[4], x)
+    xl = torch.from_numpy(x[op.c0:op.c1].copy()).cuda()
+    yl = torch.zeros(op.local_rows, dtype=torch.float64, device="cuda")
+    op.apply(xl, yl)
+    torch.cuda.synchronize()
+    good = bool(np.all(np.abs(yl.cpu().numpy() - want[op.c0:op.c1]) <= 1e-12 * 52 * 2))
+    ok = ok and good and op.mode == "halo"
+    # ---- SpGEMM: A cut by work, B broadcast -----------------------------------------------------------------------
+    A = laplacian_2d(40)
+    total, work = oracle.intprod(A[2], A[3], A[2])
+    prefix = np.zeros(A[0] + 1, dtype=np.int64)
+    np.cumsum(work, out=prefix[1:])
+    cuts = partition_rows(prefix, world)
+    c0, c1 = cuts[rank], cuts[rank + 1]
+    s, e = int(A[2][c0]), int(A[2][c1])
+    A_local = g4s_b200.CSR(c1 - c0, A[1], A[2][c0:c1 + 1] - s, A[3][s:e], A[4][s:e])
+    B = g4s_b200.CSR(A[0], A[1], A[2], A[3], A[4]) if rank == 0 else None
+    mm = DistSpGEMM(A_local, B, cuts)
+    C_local, offset = mm.multiply()
+    C_local = C_local.to_host()
+    rpt, col, val = oracle.hash_spgemm(A, A)
+    good = (offset == int(rpt[c0]) and mm.global_nnz == len(col)
+            and np.array_equal(C_local.rowptr + offset, rpt[c0:c1 + 1])
+            and np.array_equal(C_local.colids, col[rpt[c0]:rpt[c1]])
+            and np.allclose(C_local.values, val[rpt[c0]:rpt[c1]], rtol=1e-12, atol=1e-12))
+    if not good:
+        print("rank %d: spgemm mismatch" % rank, flush=True)
+    ok = ok and good
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
