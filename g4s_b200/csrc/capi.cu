@@ -35,6 +35,11 @@ int ensure_device() {
         return fail(G4S_ERR_CUDA, "g4s_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
                                       std::to_string(prop.minor) + " (there is no fallback path)");
     g_sm_count[dev] = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {  // keep freed scratch cached across calls
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g_dev_ok[dev] = 1;
     return G4S_OK;
 }
@@ -201,7 +206,12 @@ int g4s_csr_create_device(g4s_csr_t *out, int rows, int cols, const int *rowptr_
 int g4s_csr_destroy(g4s_csr_t h) {
     if (!h) return G4S_OK;
     spmv_free_plan(h);
-    if (h->owns) {
+    if (h->owns && h->pooled) {
+        cudaDeviceSynchronize();  // cudaFree's implicit guarantee: nothing in flight still uses the arrays
+        if (h->rowptr) cudaFreeAsync(h->rowptr, 0);
+        if (h->colids) cudaFreeAsync(h->colids, 0);
+        if (h->values) cudaFreeAsync(h->values, 0);
+    } else if (h->owns) {
         if (h->rowptr) cudaFree(h->rowptr);
         if (h->colids) cudaFree(h->colids);
         if (h->values) cudaFree(h->values);

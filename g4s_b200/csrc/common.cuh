@@ -58,6 +58,7 @@ struct g4s_csr {
     int *colids = nullptr;
     double *values = nullptr;
     bool owns = false;
+    bool pooled = false;  // arrays came from cudaMallocAsync (stream-ordered pool) rather than cudaMalloc
     g4s::SpmvPlan plan;
     // row-compressed blocks (off-diagonal part of a multi-GPU row block): local row r is row row_map[r] of a
     // block with full_rows rows

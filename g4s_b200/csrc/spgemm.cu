@@ -51,10 +51,15 @@ __host__ __device__ inline int work_class(int work, int cols) {
 __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restrict__ acol,
                                 const int *__restrict__ brpt, int M, int cols, int *__restrict__ row_work,
                                 unsigned long long *__restrict__ total, int *__restrict__ class_count) {
+    // class_count: [NCLASS] histogram, then [NCLASS] cursors (unused here), then [1] max work
     __shared__ int hist[NCLASS];
     __shared__ unsigned long long bsum;
+    __shared__ int bmax;
     if (threadIdx.x < NCLASS) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) bsum = 0;
+    if (threadIdx.x == 0) {
+        bsum = 0;
+        bmax = 0;
+    }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     long long w = 0;
@@ -65,7 +70,10 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
         }
         const int wi = w > 2147483647LL ? 2147483647 : (int)w;
         if (row_work) row_work[i] = wi;
-        if (class_count) atomicAdd(&hist[work_class(wi, cols)], 1);
+        if (class_count) {
+            atomicAdd(&hist[work_class(wi, cols)], 1);
+            if (wi) atomicMax(&bmax, wi);
+        }
     }
     unsigned long long s = (unsigned long long)w;
 #pragma unroll
@@ -74,6 +82,7 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
     __syncthreads();
     if (threadIdx.x == 0 && bsum) atomicAdd(total, bsum);
     if (class_count && threadIdx.x < NCLASS && hist[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+    if (class_count && threadIdx.x == 0 && bmax) atomicMax(&class_count[2 * NCLASS], bmax);
 }
 
 // rows of each class, ascending inside a block of 256 rows; blocks reserve their ranges with one atomic per class
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
 
     for (int base = blockIdx.x * RPC; base < nlist; base += gridDim.x * RPC) {
         const int idx = base + g;
-        const int row = idx < nlist ? __ldg(list + idx) : -1;
+        const int row = idx < nlist ? (list ? __ldg(list + idx) : idx) : -1;
         for (int s = lane; s < TABLE; s += GROUP) {
             mykeys[s] = -1;
             if (NUMERIC) myvals[s] = 0.0;
@@ -237,6 +246,138 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
     }
 }
 
+// class 1 (w <= 32): ONE THREAD PER ROW.  Each thread owns a private 32-slot table laid out slot-major
+// ([slot][thread]) in shared memory, so a thread only ever touches its own bank: no conflicts, no atomics.
+// Products are inserted in the reference's order (j over A's row, p over B's row) with the reference's
+// arithmetic (separate multiply, then  product + old , hash_mult.h:579-600), so these rows' VALUES are
+// bit-identical to HashSpGEMM<false,true>, not just their pattern.
+template <int TABLE, int THREADS, bool NUMERIC>
+__global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
+                                                                    int nlist) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    double *vals = reinterpret_cast<double *>(sm);                              // [TABLE][THREADS] (numeric)
+    int *keys = reinterpret_cast<int *>(vals + (NUMERIC ? TABLE * THREADS : 0));  // [TABLE][THREADS]
+    const int t = threadIdx.x, lane = t & 31;
+    constexpr int PF = 8;  // entries of a B row fetched ahead of their insertion
+    // every warp runs the same number of iterations (the cooperative store below is warp-collective)
+    for (long long base = (long long)blockIdx.x * THREADS; base < nlist; base += (long long)gridDim.x * THREADS) {
+        const long long idx = base + t;
+        const bool active = idx < nlist;
+        const int row = active ? (list ? __ldg(list + idx) : (int)idx) : -1;
+#pragma unroll
+        for (int h = 0; h < TABLE; ++h) keys[h * THREADS + t] = -1;
+        int nz = 0;
+        if (active) {
+            const int as = __ldg(a.arpt + row), ae = __ldg(a.arpt + row + 1);
+            for (int j = as; j < ae; ++j) {
+                const int k = __ldg(a.acol + j);
+                const int bs = __ldg(a.brpt + k), be = __ldg(a.brpt + k + 1);
+                double av = 0.0;
+                if (NUMERIC) av = __ldg(a.aval + j);
+                for (int p0 = bs; p0 < be; p0 += PF) {
+                    int kk[PF];
+                    double vv[PF];
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        kk[u] = -1;
+                        vv[u] = 0.0;
+                        if (p0 + u < be) {
+                            kk[u] = __ldg(a.bcol + p0 + u);
+                            if (NUMERIC) vv[u] = __ldg(a.bval + p0 + u);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        if (p0 + u < be) {
+                            const int key = kk[u];
+                            double prod = 0.0;
+                            if (NUMERIC) prod = __dmul_rn(av, vv[u]);
+                            int h = (key * HASH_MULT) & (TABLE - 1);
+                            for (;;) {
+                                const int cur = keys[h * THREADS + t];
+                                if (cur == key) {
+                                    if (NUMERIC) vals[h * THREADS + t] = __dadd_rn(prod, vals[h * THREADS + t]);
+                                    break;
+                                }
+                                if (cur == -1) {
+                                    keys[h * THREADS + t] = key;
+                                    if (NUMERIC) vals[h * THREADS + t] = prod;
+                                    ++nz;
+                                    break;
+                                }
+                                h = (h + 1) & (TABLE - 1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!NUMERIC) {
+            if (active) a.row_nnz[row] = nz;
+            continue;
+        }
+        // compact in place (the prefix [0, n) never overtakes the slot being read)
+        int n = 0;
+#pragma unroll 8
+        for (int h = 0; h < TABLE; ++h) {
+            const int key = keys[h * THREADS + t];
+            if (key != -1) {
+                const double v = vals[h * THREADS + t];
+                keys[n * THREADS + t] = key;
+                vals[n * THREADS + t] = v;
+                ++n;
+            }
+        }
+        const int out = active ? __ldg(a.crpt + row) : 0;
+        const int row0 = __shfl_sync(0xffffffffu, row, 0);
+        // Fast store: the warp's 32 rows are consecutive (their output is one contiguous range of C) and every
+        // row fits the upper half of its table.  Entries are rank-sorted into that upper half, skewed by
+        // (lane + e) so that the warp can then read them back conflict-free and store C fully coalesced.
+        const bool fast = __all_sync(0xffffffffu, active && row == row0 + lane && n <= TABLE / 2);
+        __syncwarp();
+        if (fast) {
+            const int tw = t - lane;  // first thread of this warp
+            for (int e = 0; e < n; ++e) {
+                const int key = keys[e * THREADS + t];
+                int rank = 0;
+                for (int f = 0; f < n; ++f) rank += keys[f * THREADS + t] < key;
+                const int col = tw + ((lane + rank) & 31);
+                keys[(TABLE / 2 + rank) * THREADS + col] = key;
+                vals[(TABLE / 2 + rank) * THREADS + col] = vals[e * THREADS + t];
+            }
+            __syncwarp();
+            const int out0 = __shfl_sync(0xffffffffu, out, 0);
+            const int out1 = __shfl_sync(0xffffffffu, out + n, 31);
+            for (int ob = out0; ob < out1; ob += 32) {  // warp-uniform trip count: the search uses shuffles
+                const int o = min(ob + lane, out1 - 1);
+                int lo = 0, hi = 31;  // owner lane = last lane whose row starts at or before o
+#pragma unroll
+                for (int step = 0; step < 5; ++step) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    const int start_mid = __shfl_sync(0xffffffffu, out, mid);
+                    if (start_mid <= o) lo = mid;
+                    else hi = mid - 1;
+                }
+                const int e = o - __shfl_sync(0xffffffffu, out, lo);
+                if (ob + lane < out1) {
+                    const int col = tw + ((lo + e) & 31);
+                    a.ccol[o] = keys[(TABLE / 2 + e) * THREADS + col];
+                    a.cval[o] = vals[(TABLE / 2 + e) * THREADS + col];
+                }
+            }
+            __syncwarp();
+        } else if (active) {
+            for (int e = 0; e < n; ++e) {
+                const int key = keys[e * THREADS + t];
+                int rank = 0;
+                for (int f = 0; f < n; ++f) rank += keys[f * THREADS + t] < key;
+                a.ccol[out + rank] = key;
+                a.cval[out + rank] = vals[e * THREADS + t];
+            }
+        }
+    }
+}
+
 // class 5: tables in global memory.  Persistent CTAs; CTA b owns slab b (slab_slots entries) and re-initialises
 // only the power-of-two prefix the current row needs.
 template <bool NUMERIC>
@@ -251,7 +392,7 @@ __global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a,
     const int SUB = 1 << sub_lg, nsub = blockDim.x >> sub_lg, my_sub = threadIdx.x >> sub_lg,
               sl = threadIdx.x & (SUB - 1);
     for (int idx = blockIdx.x; idx < nlist; idx += gridDim.x) {
-        const int row = list[idx];
+        const int row = list ? list[idx] : idx;
         const int w = min(row_work[row], a.N);
         long long tsize = 16384;
         while (tsize < 2LL * w) tsize <<= 1;
@@ -347,9 +488,31 @@ static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, bool num
     return G4S_OK;
 }
 
+template <int TABLE, int THREADS>
+static int launch_thread_row(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
+    if (nlist == 0) return G4S_OK;
+    const size_t smem_sym = sizeof(int) * TABLE * THREADS;
+    const size_t smem_num = (sizeof(int) + sizeof(double)) * TABLE * THREADS;
+    auto ks = spgemm_thread_row_kernel<TABLE, THREADS, false>;
+    auto kn = spgemm_thread_row_kernel<TABLE, THREADS, true>;
+    static bool configured = false;
+    if (!configured) {
+        G4S_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sym));
+        G4S_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_num));
+        configured = true;
+    }
+    const long long want = ((long long)nlist + THREADS - 1) / THREADS;
+    const int grid = (int)std::min<long long>(want, (long long)sm_count() * 32);
+    if (numeric) kn<<<grid, THREADS, smem_num, stream>>>(a, list, nlist);
+    else ks<<<grid, THREADS, smem_sym, stream>>>(a, list, nlist);
+    G4S_CHECK_LAUNCH("spgemm_thread_row_kernel");
+    return G4S_OK;
+}
+
 struct Bins {
     int *row_work = nullptr;
     int *perm = nullptr;
+    bool identity = false;  // every non-empty row is in one class: lists are 0..M-1, no permutation built
     int count[NCLASS] = {0};
     int offset[NCLASS + 1] = {0};
     long long total_work = 0;
@@ -359,87 +522,106 @@ struct Bins {
 static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab_keys, double *slab_vals,
                      long long slab_slots, int slab_ctas, cudaStream_t stream) {
     int rc;
-    if ((rc = launch_smem<4, 32, 32, 256>(a, b.perm + b.offset[1], b.count[1], numeric, stream))) return rc;
-    if ((rc = launch_smem<32, 512, 256, 256>(a, b.perm + b.offset[2], b.count[2], numeric, stream))) return rc;
-    if ((rc = launch_smem<256, 4096, 2048, 256>(a, b.perm + b.offset[3], b.count[3], numeric, stream))) return rc;
-    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, b.perm + b.offset[4], b.count[4], numeric, stream))) return rc;
+    auto list = [&](int c) -> const int * { return b.identity ? nullptr : b.perm + b.offset[c]; };
+    if ((rc = launch_thread_row<32, 128>(a, list(1), b.count[1], numeric, stream))) return rc;
+    if ((rc = launch_smem<32, 512, 256, 256>(a, list(2), b.count[2], numeric, stream))) return rc;
+    if ((rc = launch_smem<256, 4096, 2048, 256>(a, list(3), b.count[3], numeric, stream))) return rc;
+    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, list(4), b.count[4], numeric, stream))) return rc;
     if (b.count[5]) {
         if (numeric)
-            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, b.perm + b.offset[5], b.count[5], b.row_work,
+            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(5), b.count[5], b.row_work,
                                                                       slab_keys, slab_vals, slab_slots);
         else
-            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, b.perm + b.offset[5], b.count[5], b.row_work,
+            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, list(5), b.count[5], b.row_work,
                                                                        slab_keys, slab_vals, slab_slots);
         G4S_CHECK_LAUNCH("spgemm_global_kernel");
     }
     return G4S_OK;
 }
 
-__global__ void max_work_kernel(const int *__restrict__ row_work, int M, int *__restrict__ out) {
-    int m = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x)
-        m = max(m, row_work[i]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
+// Scratch reused across calls on the calling thread (row work, row lists, counters): SpGEMM is called in loops
+// (the reference's driver runs it 11 times, mm/src/mkl_spgemm.cpp:67-79) and cudaMalloc is a device-wide sync.
+struct Workspace {
+    int device = -1;
+    size_t rows_cap = 0;
+    int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
+    unsigned long long *dtotal = nullptr;
+    int *hcount = nullptr;  // pinned
+    unsigned long long *htotal = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ensure(int M) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != device) {  // one workspace per thread; a device switch starts over
+            *this = Workspace();
+            device = dev;
+        }
+        if (!dcount) {
+            G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (2 * NCLASS + 1)));
+            G4S_CUDA(cudaMalloc(&dtotal, sizeof(unsigned long long)));
+            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (2 * NCLASS + 1)));
+            G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
+            for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
+        }
+        if ((size_t)M + 1 > rows_cap) {
+            if (row_work) cudaFree(row_work);
+            if (perm) cudaFree(perm);
+            if (row_nnz) cudaFree(row_nnz);
+            rows_cap = (size_t)M + 1;
+            G4S_CUDA(cudaMalloc(&row_work, sizeof(int) * rows_cap));
+            G4S_CUDA(cudaMalloc(&perm, sizeof(int) * rows_cap));
+            G4S_CUDA(cudaMalloc(&row_nnz, sizeof(int) * rows_cap));
+        }
+        return G4S_OK;
+    }
+};
+static thread_local Workspace t_ws;
 
 int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     if (A->cols != B->rows) return fail(G4S_ERR_SHAPE, "g4s_spgemm: A.cols != B.rows");
     const int M = A->rows, N = B->cols;
-    cudaEvent_t ev[5];
-    for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
-    G4S_CUDA(cudaEventRecord(ev[0], stream));
+    Workspace &ws = t_ws;
+    int rc = ws.ensure(M);
+    if (rc) return rc;
+    G4S_CUDA(cudaEventRecord(ws.ev[0], stream));
 
-    // ---- binning --------------------------------------------------------------------------------------
+    // ---- binning (BIN::set_max_bin) -------------------------------------------------------------------------
     Bins b;
-    int *dcount = nullptr;  // [NCLASS] counts, [NCLASS] cursors, [1] max
-    unsigned long long *dtotal = nullptr;
-    int *row_nnz = nullptr;
-    G4S_CUDA(cudaMallocAsync(&b.row_work, sizeof(int) * (size_t)std::max(M, 1), stream));
-    G4S_CUDA(cudaMallocAsync(&b.perm, sizeof(int) * (size_t)std::max(M, 1), stream));
-    G4S_CUDA(cudaMallocAsync(&row_nnz, sizeof(int) * ((size_t)M + 1), stream));
-    G4S_CUDA(cudaMallocAsync(&dcount, sizeof(int) * (2 * NCLASS + 1), stream));
-    G4S_CUDA(cudaMallocAsync(&dtotal, sizeof(unsigned long long), stream));
+    b.row_work = ws.row_work;
+    b.perm = ws.perm;
+    int *row_nnz = ws.row_nnz;
+    int *dcount = ws.dcount;
     G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int) * (2 * NCLASS + 1), stream));
-    G4S_CUDA(cudaMemsetAsync(dtotal, 0, sizeof(unsigned long long), stream));
+    G4S_CUDA(cudaMemsetAsync(ws.dtotal, 0, sizeof(unsigned long long), stream));
     const int threads = 256;
     const int blocks = (M + threads - 1) / threads;
     if (M > 0) {
-        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, dtotal, dcount);
+        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, ws.dtotal, dcount);
         G4S_CHECK_LAUNCH("row_work_kernel");
-        max_work_kernel<<<sm_count() * 4, 256, 0, stream>>>(b.row_work, M, dcount + 2 * NCLASS);
-        G4S_CHECK_LAUNCH("max_work_kernel");
     }
-    int hcount[2 * NCLASS + 1];
-    unsigned long long htotal = 0;
-    G4S_CUDA(cudaMemcpyAsync(hcount, dcount, sizeof(hcount), cudaMemcpyDeviceToHost, stream));
-    G4S_CUDA(cudaMemcpyAsync(&htotal, dtotal, sizeof(htotal), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaMemcpyAsync(ws.hcount, dcount, sizeof(int) * (2 * NCLASS + 1), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaMemcpyAsync(ws.htotal, ws.dtotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     G4S_CUDA(cudaStreamSynchronize(stream));
-    b.total_work = (long long)htotal;
-    b.max_work = hcount[2 * NCLASS];
-    for (int c = 0; c < NCLASS; ++c) {
-        b.count[c] = hcount[c];
-        b.offset[c + 1] = b.offset[c] + (c ? hcount[c] : 0);
-    }
-    b.offset[0] = 0;
-    {   // cursors start at each class's offset (class 0 rows are not listed)
-        int cur[NCLASS];
+    b.total_work = (long long)*ws.htotal;
+    b.max_work = ws.hcount[2 * NCLASS];
+    int cur[NCLASS];
+    {
         int off = 0;
         for (int c = 0; c < NCLASS; ++c) {
+            b.count[c] = ws.hcount[c];
             cur[c] = off;
             b.offset[c] = off;
             if (c) off += b.count[c];
+            if (c && b.count[c] == M && M > 0) b.identity = true;
         }
         b.offset[NCLASS] = off;
-        b.offset[0] = 0;
-        G4S_CUDA(cudaMemcpyAsync(dcount + NCLASS, cur, sizeof(cur), cudaMemcpyHostToDevice, stream));
     }
-    if (M > 0) {
+    if (M > 0 && !b.identity) {
+        G4S_CUDA(cudaMemcpyAsync(dcount + NCLASS, cur, sizeof(cur), cudaMemcpyHostToDevice, stream));
         bin_fill_kernel<<<blocks, threads, 0, stream>>>(b.row_work, M, N, dcount + NCLASS, b.perm, row_nnz);
         G4S_CHECK_LAUNCH("bin_fill_kernel");
     }
-    G4S_CUDA(cudaEventRecord(ev[1], stream));
+    G4S_CUDA(cudaEventRecord(ws.ev[1], stream));
 
     // lanes per row of B: next power of two >= B's mean row length
     int sub_lg = 0;
@@ -478,25 +660,32 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     a.row_nnz = row_nnz;
     a.sub_lg = sub_lg;
 
-    // ---- symbolic ---------------------------------------------------------------------------------------
-    int rc = run_phase(a, b, false, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
+    // ---- symbolic ---------------------------------------------------------------------------------------------
+    rc = run_phase(a, b, false, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
     if (rc) return rc;
-    G4S_CUDA(cudaEventRecord(ev[2], stream));
+    G4S_CUDA(cudaEventRecord(ws.ev[2], stream));
 
-    // ---- row pointers + allocation ------------------------------------------------------------------------
+    // ---- row pointers (scan straight into C) + allocation of C's arrays from the stream-ordered pool --------------
+    g4s_csr *C = new (std::nothrow) g4s_csr();
+    if (!C) return fail(G4S_ERR_ALLOC, "host allocation failed");
+    C->rows = M;
+    C->cols = N;
+    C->owns = true;
+    C->pooled = true;
+    G4S_CUDA(cudaMallocAsync(&C->rowptr, sizeof(int) * ((size_t)M + 1) + 64, stream));
     long long cnnz = 0;
-    int *crpt_tmp = nullptr;
-    G4S_CUDA(cudaMallocAsync(&crpt_tmp, sizeof(int) * ((size_t)M + 1), stream));
-    rc = exclusive_scan_i32(row_nnz, crpt_tmp, M, 1, &cnnz, stream);
-    if (rc) return rc;
-    if (cnnz > 2147483647LL) return fail(G4S_ERR_INVALID, "g4s_spgemm: nnz(C) exceeds int32 row pointers");
-    g4s_csr *C = nullptr;
-    rc = alloc_csr(&C, M, N, cnnz);
-    if (rc) return rc;
-    G4S_CUDA(cudaMemcpyAsync(C->rowptr, crpt_tmp, sizeof(int) * ((size_t)M + 1), cudaMemcpyDeviceToDevice, stream));
-    G4S_CUDA(cudaEventRecord(ev[3], stream));
+    rc = exclusive_scan_i32(row_nnz, C->rowptr, M, 1, &cnnz, stream);
+    if (rc == G4S_OK && cnnz > 2147483647LL) rc = fail(G4S_ERR_INVALID, "g4s_spgemm: nnz(C) exceeds int32 row pointers");
+    if (rc) {
+        g4s_csr_destroy(C);
+        return rc;
+    }
+    C->nnz = cnnz;
+    G4S_CUDA(cudaMallocAsync(&C->colids, sizeof(int) * (size_t)cnnz + 64, stream));
+    G4S_CUDA(cudaMallocAsync(&C->values, sizeof(double) * (size_t)cnnz + 64, stream));
+    G4S_CUDA(cudaEventRecord(ws.ev[3], stream));
 
-    // ---- numeric ------------------------------------------------------------------------------------------
+    // ---- numeric ----------------------------------------------------------------------------------------------
     a.crpt = C->rowptr;
     a.ccol = C->colids;
     a.cval = C->values;
@@ -505,23 +694,15 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
         g4s_csr_destroy(C);
         return rc;
     }
-    G4S_CUDA(cudaEventRecord(ev[4], stream));
-
-    G4S_CUDA(cudaFreeAsync(crpt_tmp, stream));
+    G4S_CUDA(cudaEventRecord(ws.ev[4], stream));
     if (slab_keys) G4S_CUDA(cudaFreeAsync(slab_keys, stream));
     if (slab_vals) G4S_CUDA(cudaFreeAsync(slab_vals, stream));
-    G4S_CUDA(cudaFreeAsync(b.row_work, stream));
-    G4S_CUDA(cudaFreeAsync(b.perm, stream));
-    G4S_CUDA(cudaFreeAsync(row_nnz, stream));
-    G4S_CUDA(cudaFreeAsync(dcount, stream));
-    G4S_CUDA(cudaFreeAsync(dtotal, stream));
     G4S_CUDA(cudaStreamSynchronize(stream));
     for (int i = 0; i < 4; ++i) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        cudaEventElapsedTime(&ms, ws.ev[i], ws.ev[i + 1]);
         t_phase_ms[i] = ms;
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     *Cout = C;
     return G4S_OK;
 }
