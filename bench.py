@@ -199,27 +199,45 @@ def run_ours(args, rank, world):
     else:
         from g4s_b200.dist import DistSpMV
 
-        op = DistSpMV.laplacian3d27(n, dist.group.WORLD)
+        op = DistSpMV.laplacian3d27(n, dist.group.WORLD, mode=args.mode)
         x_host = torch.empty(op.local_rows, dtype=torch.float64).pin_memory()
         x_host.numpy()[:] = np.random.default_rng(12345 + rank).uniform(-1.0, 1.0, op.local_rows)
         y_host = torch.empty(op.local_rows, dtype=torch.float64).pin_memory()
         x = x_host.cuda(non_blocking=True)
         y = torch.empty(op.local_rows, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
+        if op.mode == "peer":  # x lives in the rank's two CUDA-IPC-shared buffers; products alternate between them
+            for xb in op.x_buffers:
+                xb.copy_(x)
 
-        def step():
-            op.apply(x, y)
+            def step():
+                op.apply(op.next_x(), y)
 
-        def e2e_step():
-            x.copy_(x_host, non_blocking=True)
-            op.apply(x, y)
-            y_host.copy_(y, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            def e2e_step():
+                xb = op.next_x()
+                xb.copy_(x_host, non_blocking=True)
+                op.apply(xb, y)
+                y_host.copy_(y, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        else:
+            def step():
+                op.apply(x, y)
+
+            def e2e_step():
+                x.copy_(x_host, non_blocking=True)
+                op.apply(x, y)
+                y_host.copy_(y, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
         h2d, d2h = 8 * rows_total, 8 * rows_total  # summed over ranks
         launches_per_step = op.launches_per_step
-        parallelism = "rows cut by nnz over %d GPUs; halo of x exchanged over NCCL, overlapped with the " \
-                      "diagonal-block product" % world
+        parallelism = {
+            "peer": "rows cut by nnz over %d GPUs; ONE fused SpMV kernel per GPU loads remote x entries over NVLink from "
+                    "CUDA-IPC peer memory; a 4-byte NCCL all-reduce per step is the barrier",
+            "halo": "rows cut by nnz over %d GPUs; halo of x exchanged with NCCL all_to_all, overlapped with the "
+                    "diagonal-block product",
+            "allgather": "rows cut by nnz over %d GPUs; x assembled with NCCL all-gather, overlapped with the "
+                         "diagonal-block product"}[op.mode] % world
 
     def barrier():
         if dist is not None:
@@ -372,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_GRID, help="grid edge (default 400 = BASELINE configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget at N=1")
+    ap.add_argument("--mode", default="peer", choices=["peer", "halo", "allgather", "auto"],
+                    help="multi-GPU x assembly (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spgemm", action="store_true")
     args = ap.parse_args()

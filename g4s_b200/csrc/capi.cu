@@ -50,7 +50,11 @@ int sm_count() {
     return (dev >= 0 && dev < 64 && g_sm_count[dev] > 0) ? g_sm_count[dev] : 148;
 }
 
-int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream);
+struct XParts;
+int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
+             const XParts *parts = nullptr);
+int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
+                         cudaStream_t stream);
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream);
 void spmv_free_plan(g4s_csr *h);
 
@@ -262,6 +266,44 @@ int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const in
     if (rc) return rc;
     if (!row_map_dev) row_map_dev = A->row_map;  // a row-compressed handle scatters through its own map
     return spmv_run(A, x_dev, y_dev, row_map_dev, accumulate != 0, (cudaStream_t)stream);
+}
+
+int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
+                                double *y_dev, void *stream) {
+    if (!A || !x_parts || !cuts || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_partitioned_device: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return spmv_run_partitioned(A, world, self, x_parts, cuts, y_dev, (cudaStream_t)stream);
+}
+
+// ---- peer memory (CUDA IPC): buffers that other ranks' kernels on the same box read over NVLink ------------------
+int g4s_peer_alloc(size_t bytes, void **ptr_dev, unsigned char *handle64) {
+    if (!ptr_dev || !handle64) return fail(G4S_ERR_INVALID, "g4s_peer_alloc: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    G4S_CUDA(cudaMalloc(ptr_dev, bytes ? bytes : 8));
+    cudaIpcMemHandle_t h;
+    G4S_CUDA(cudaIpcGetMemHandle(&h, *ptr_dev));
+    memcpy(handle64, &h, 64);
+    return G4S_OK;
+}
+int g4s_peer_open(const unsigned char *handle64, void **ptr_dev) {
+    if (!ptr_dev || !handle64) return fail(G4S_ERR_INVALID, "g4s_peer_open: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    G4S_CUDA(cudaIpcOpenMemHandle(ptr_dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return G4S_OK;
+}
+int g4s_peer_close(void *ptr_dev) {
+    if (ptr_dev) G4S_CUDA(cudaIpcCloseMemHandle(ptr_dev));
+    return G4S_OK;
+}
+int g4s_peer_free(void *ptr_dev) {
+    if (ptr_dev) G4S_CUDA(cudaFree(ptr_dev));
+    return G4S_OK;
 }
 
 int g4s_spmv_host(g4s_csr_t A, const double *x, double *y) {

@@ -43,6 +43,8 @@ struct SpmvPlan {
     unsigned char *lanes_lg = nullptr;  // [nchunks]   log2(lanes per row) chosen by the inspector
     double *carry = nullptr;            // [nchunks]   partial sums of non-final pieces of long rows
     int4 *long_rows = nullptr;          // [n_long]    (row, first chunk, pieces, -)
+    unsigned char *part_flags = nullptr;  // [nchunks] partitioned x: chunk references a remote column
+    int part_lo = 0, part_hi = 0;       // owned column range the flags were computed for
     int n_long = 0;                     // rows longer than cap
     int max_row_len = 0;
     int lanes_per_row = 0;              // tuning override, 0 = inspector's choice

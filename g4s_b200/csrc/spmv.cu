@@ -276,7 +276,32 @@ struct SpmvArgs {
     long long nnz;
     int nchunks;
     int force_lg;  // -1: use the inspector's choice
+    const unsigned char *part_flags;  // partitioned x: 1 where a chunk references a column another GPU owns
 };
+
+// x split over the GPUs of one NVSwitch box: part q holds x[cut[q] .. cut[q+1]) and base[q] is a pointer this GPU
+// can dereference (its own memory for q == self, CUDA-IPC-mapped peer memory otherwise).  Loads of remote entries
+// go straight over NVLink from inside the SpMV kernel: there is no separate exchange step.
+constexpr int MAX_PARTS = 8;
+struct XParts {
+    const double *base[MAX_PARTS];
+    int cut[MAX_PARTS + 1];
+    int world;
+    int lo, hi;  // this GPU's own column range and slice
+    const double *self_base;
+};
+__device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
+    if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
+    const double *b = xp.base[0];  // static indices only: the struct stays in the kernel-parameter bank
+    int cut = xp.cut[0];
+#pragma unroll
+    for (int i = 1; i < MAX_PARTS; ++i)
+        if (i < xp.world && c >= xp.cut[i]) {
+            b = xp.base[i];
+            cut = xp.cut[i];
+        }
+    return __ldg(b + (c - cut));
+}
 
 template <int CAP>
 struct alignas(32) ChunkBuf {
@@ -284,9 +309,9 @@ struct alignas(32) ChunkBuf {
     int cols[CAP + 8];
 };
 
-template <int L, int CAP, bool ACCUM>
-__device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvArgs &a, int chunk, int row0,
-                                           int row1, int nnz0, int nnz1, int lane, int rp0, int rp1) {
+template <int L, int CAP, bool ACCUM, bool PART>
+__device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvArgs &a, const XParts &xp, int chunk,
+                                           int row0, int row1, int nnz0, int nnz1, int lane, int rp0, int rp1) {
     const int a0 = nnz0 & ~3;
     const int R = row1 - row0;
     const int nloc = R > 0 ? R : 1;  // R == 0: a non-final piece of a long row (its sum goes to carry)
@@ -308,7 +333,7 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
         int k = s + sub - a0;
         const int ke = e - a0;
 #pragma unroll 4
-        for (; k < ke; k += L) acc = fma(buf.vals[k], __ldg(x + buf.cols[k]), acc);
+        for (; k < ke; k += L) acc = fma(buf.vals[k], PART ? load_x_part(xp, buf.cols[k]) : __ldg(x + buf.cols[k]), acc);
 #pragma unroll
         for (int o = L >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (sub == 0 && r < nloc) {
@@ -323,8 +348,8 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
     }
 }
 
-template <int CAP, int NBUF, int WARPS, bool ACCUM>
-__global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a) {
+template <int CAP, int NBUF, int WARPS, bool ACCUM, bool PART>
+__global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a, const XParts xp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[WARPS * NBUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,17 +413,40 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         }
         mbar_wait(&bar[b], parity);
         const ChunkBuf<CAP> &buf = bufs[b];
+        // partitioned x: only chunks that reference a remote column pay for the owner lookup; every other chunk
+        // runs the plain code on the GPU's own slice (a.x = own slice rebased to global column ids)
+        const bool remote = PART && __ldg(a.part_flags + c) != 0;
+#define G4S_CHUNK_CASE(LANES)                                                                                         \
+    if (remote) chunk_rows<LANES, CAP, ACCUM, true>(buf, a, xp, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1);       \
+    else chunk_rows<LANES, CAP, ACCUM, false>(buf, a, xp, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1);             \
+    break;
         switch (lg) {
-            case 0: chunk_rows<1, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
-            case 1: chunk_rows<2, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
-            case 2: chunk_rows<4, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
-            case 3: chunk_rows<8, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
-            case 4: chunk_rows<16, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
-            default: chunk_rows<32, CAP, ACCUM>(buf, a, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1); break;
+            case 0: G4S_CHUNK_CASE(1)
+            case 1: G4S_CHUNK_CASE(2)
+            case 2: G4S_CHUNK_CASE(4)
+            case 3: G4S_CHUNK_CASE(8)
+            case 4: G4S_CHUNK_CASE(16)
+            default: G4S_CHUNK_CASE(32)
         }
+#undef G4S_CHUNK_CASE
         __syncwarp();  // every lane is done reading slot b
         if (lane == 0 && next < a.nchunks) issue(b, n0.y, n1.y);
     }
+}
+
+// one warp per chunk: does it reference a column outside [lo, hi)?
+__global__ void chunk_remote_flags_kernel(const int2 *__restrict__ desc, const int *__restrict__ colids, int nchunks,
+                                          int lo, int hi, unsigned char *__restrict__ flags) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    const int s = desc[c].y, e = desc[c + 1].y;
+    int any = 0;
+    for (int k = s + lane; k < e; k += 32) {
+        const int col = __ldg(colids + k);
+        any |= (col < lo || col >= hi);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[c] = any ? 1 : 0;
 }
 
 // y[row] += carries of the row's non-final pieces, in piece order
@@ -433,21 +481,29 @@ __global__ void spmv_warp_row_kernel(const int *__restrict__ rowptr, const int *
 // host side
 // ------------------------------------------------------------------------------------------------------
 template <int CAP, int NBUF, int WARPS>
-static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm, cudaStream_t stream) {
+static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm, cudaStream_t stream,
+                               const XParts *parts = nullptr) {
     const size_t smem = sizeof(ChunkBuf<CAP>) * NBUF * WARPS;
-    auto k0 = spmv_chunk_kernel<CAP, NBUF, WARPS, false>;
-    auto k1 = spmv_chunk_kernel<CAP, NBUF, WARPS, true>;
+    auto k0 = spmv_chunk_kernel<CAP, NBUF, WARPS, false, false>;
+    auto k1 = spmv_chunk_kernel<CAP, NBUF, WARPS, true, false>;
+    auto kp = spmv_chunk_kernel<CAP, NBUF, WARPS, false, true>;
     static bool configured = false;
     if (!configured) {
         G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     long long want = ((long long)args.nchunks + WARPS - 1) / WARPS;
     int grid = (int)std::min<long long>(want, (long long)sm_count() * ctas_per_sm);
     if (grid < 1) grid = 1;
-    if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args);
-    else k0<<<grid, WARPS * 32, smem, stream>>>(args);
+    XParts none;
+    none.world = 0;
+    none.lo = none.hi = 0;
+    none.self_base = nullptr;
+    if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
+    else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
+    else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
     G4S_CHECK_LAUNCH("spmv_chunk_kernel");
     return G4S_OK;
 }
@@ -501,19 +557,21 @@ void spmv_free_plan(g4s_csr *h) {
     if (p.lanes_lg) cudaFree(p.lanes_lg);
     if (p.carry) cudaFree(p.carry);
     if (p.long_rows) cudaFree(p.long_rows);
+    if (p.part_flags) cudaFree(p.part_flags);
     const int lanes = p.lanes_per_row, variant = p.variant;
     p = SpmvPlan();
     p.lanes_per_row = lanes;
     p.variant = variant;
 }
 
-int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream) {
+int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
+             const XParts *parts) {
     if (h->rows == 0) return G4S_OK;
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     const SpmvPlan &p = h->plan;
     if (p.variant == 9) {  // comparison baseline
-        if (accum || row_map) return fail(G4S_ERR_INVALID, "warp-per-row baseline supports plain y = A x only");
+        if (accum || row_map || parts) return fail(G4S_ERR_INVALID, "warp-per-row baseline supports plain y = A x only");
         spmv_warp_row_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->colids, h->values, x, y, h->rows);
         G4S_CHECK_LAUNCH("spmv_warp_row_kernel");
         return G4S_OK;
@@ -532,6 +590,8 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     a.nnz = h->nnz;
     a.nchunks = p.nchunks;
     a.force_lg = -1;
+    a.part_flags = nullptr;
+    a.part_flags = parts ? p.part_flags : nullptr;
     if (p.lanes_per_row > 0) {
         int lg = 0;
         while ((1 << lg) < p.lanes_per_row && lg < 5) ++lg;
@@ -540,13 +600,13 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     // kernel shapes: ring depth x warps per CTA x CTAs per SM.  Measured on B200, 3-D 27-point n=400
     // (profiles/r01_spmv_sweep.txt): 18 single-buffered warps per SM as 2 CTAs of 9 is the fastest; deeper
     // per-warp rings with fewer warps lose (resident warps, not per-warp prefetch depth, hide the latency).
-    switch (p.variant) {
+    switch (parts ? 0 : p.variant) {
         case 1: rc = launch_chunk_kernel<SPMV_CAP, 1, 16>(a, accum, 1, stream); break;
         case 2: rc = launch_chunk_kernel<SPMV_CAP, 2, 8>(a, accum, 1, stream); break;
         case 3: rc = launch_chunk_kernel<SPMV_CAP, 2, 4>(a, accum, 2, stream); break;
         case 4: rc = launch_chunk_kernel<SPMV_CAP, 1, 8>(a, accum, 2, stream); break;
         case 5: rc = launch_chunk_kernel<SPMV_CAP, 1, 6>(a, accum, 3, stream); break;
-        default: rc = launch_chunk_kernel<SPMV_CAP, 1, 9>(a, accum, 2, stream); break;
+        default: rc = launch_chunk_kernel<SPMV_CAP, 1, 9>(a, accum, 2, stream, parts); break;
     }
     if (rc) return rc;
     if (p.n_long > 0) {
@@ -554,6 +614,34 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
         G4S_CHECK_LAUNCH("spmv_long_fixup_kernel");
     }
     return G4S_OK;
+}
+
+int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
+                         cudaStream_t stream) {
+    if (world < 1 || world > MAX_PARTS || self < 0 || self >= world)
+        return fail(G4S_ERR_INVALID, "partitioned SpMV supports 1..8 parts (one NVSwitch box)");
+    XParts xp;
+    for (int q = 0; q < MAX_PARTS; ++q) xp.base[q] = q < world ? x_parts[q] : nullptr;
+    for (int q = 0; q <= MAX_PARTS; ++q) xp.cut[q] = cuts[q < world ? q : world];
+    xp.world = world;
+    xp.lo = cuts[self];
+    xp.hi = cuts[self + 1];
+    xp.self_base = x_parts[self];
+    int rc = spmv_build_plan(h, stream);
+    if (rc) return rc;
+    SpmvPlan &p = h->plan;
+    if (!p.part_flags || p.part_lo != xp.lo || p.part_hi != xp.hi) {  // once per (matrix, owned range)
+        if (!p.part_flags) G4S_CUDA(cudaMalloc(&p.part_flags, (size_t)p.nchunks + 1));
+        if (p.nchunks) {
+            chunk_remote_flags_kernel<<<(int)(((long long)p.nchunks * 32 + 255) / 256), 256, 0, stream>>>(
+                p.desc, h->colids, p.nchunks, xp.lo, xp.hi, p.part_flags);
+            G4S_CHECK_LAUNCH("chunk_remote_flags_kernel");
+        }
+        p.part_lo = xp.lo;
+        p.part_hi = xp.hi;
+    }
+    // the plain path indexes x by global column id: rebase the own slice (never dereferenced outside [lo, hi))
+    return spmv_run(h, x_parts[self] - xp.lo, y, nullptr, false, stream, &xp);
 }
 
 }  // namespace g4s

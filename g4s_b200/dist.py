@@ -9,6 +9,12 @@ DIAGONAL block (columns it owns) and the row-compressed OFF-DIAGONAL block.  Eve
     main stream : y  = A_diag x_local                      (overlaps the exchange)
                   y += A_off  halo                         (after the exchange event)
 
+"peer" mode (one NVSwitch box, <= 8 GPUs) removes the exchange altogether: every rank keeps its x slice in a
+CUDA-IPC-shared buffer, the row block is NOT split, and ONE SpMV kernel loads the entries owned by other GPUs
+straight from their memory over NVLink while it streams its own matrix (g4s_spmv_partitioned_device).  A tiny
+all-reduce per product is the barrier that orders it after every rank has written its slice; x is double-buffered
+so that the barrier of product k+1 also covers "everyone is done reading the buffer of product k-1".
+
 "halo" mode moves only the x entries that are referenced (for a stencil: two planes per neighbour instead of the
 whole vector); "allgather" mode is the plain NCCL all-gather of x named in BASELINE.json's north_star and is the
 fallback for matrices whose off-diagonal block references most of x (R-MAT).
@@ -124,6 +130,10 @@ class DistSpMV:
         self.local_rows = self.c1 - self.c0
         assert A_local.rows == self.local_rows, "A_local must hold exactly this rank's rows"
         dev = self.ops.device
+        self.comm_stream = None
+        if mode == "peer":
+            self._init_peer(A_local, dev)
+            return
         self.diag, self.off = self.ops.split(A_local, self.c0, self.c1)
         # how much of x the off-diagonal block references decides the exchange
         needed = self.ops.compact(self.off)
@@ -160,7 +170,57 @@ class DistSpMV:
             self.halo = torch.empty(self.slot * self.world, dtype=torch.float64, device=dev)
             self.exchange_bytes = 8 * self.slot * (self.world - 1)
         self.comm_stream = torch.cuda.Stream() if self.ops.device_type == "cuda" else None
+        self._k = 0
         self.launches_per_step = 1 + (1 if self.off.rows else 0) + (1 if self.mode == "halo" and self.send_idx.numel() else 0)
+
+    def _init_peer(self, A_local, dev):
+        if self.world > 8:
+            raise ValueError("peer mode supports up to 8 GPUs (one NVSwitch box)")
+        L = lib()
+        self.mode = "peer"
+        self.A = A_local
+        self._own, mine = [], []
+        for _ in range(2):
+            ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+            check(L.g4s_peer_alloc(C.c_size_t(8 * max(self.local_rows, 1)), C.byref(ptr), h))
+            self._own.append(ptr.value)
+            mine.append(bytes(h))
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=self.group)
+        self._opened, self._parts = [], []
+        for b in range(2):
+            arr = (C.c_void_p * self.world)()
+            for q in range(self.world):
+                if q == self.rank:
+                    arr[q] = self._own[b]
+                else:
+                    p = C.c_void_p()
+                    check(L.g4s_peer_open((C.c_ubyte * 64).from_buffer_copy(every[q][b]), C.byref(p)))
+                    arr[q] = p.value
+                    self._opened.append(p.value)
+            self._parts.append(arr)
+        self.x_buffers = [torch.as_tensor(_DevArray(self._own[b], max(self.local_rows, 1), "<f8"), device=dev)[:self.local_rows]
+                          for b in range(2)]
+        self._cuts_c = (C.c_int * (self.world + 1))(*self.cuts)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._k = 0
+        self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 1
+        dist.barrier(group=self.group)
+
+    def next_x(self):
+        """peer mode: the shared buffer the next apply() will read; fill it in place to skip apply()'s copy."""
+        return self.x_buffers[self._k % 2]
+
+    def close(self):
+        if getattr(self, "mode", None) == "peer" and self._own:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                lib().g4s_peer_close(C.c_void_p(p))
+            dist.barrier(group=self.group)
+            for p in self._own:
+                lib().g4s_peer_free(C.c_void_p(p))
+            self._own, self._opened = [], []
 
     # -- convenience constructors ----------------------------------------------------------------------------
     @classmethod
@@ -174,7 +234,8 @@ class DistSpMV:
         r = dist.get_rank(group)
         A_local = CSR.laplacian3d27(n, cuts[r], cuts[r + 1])
         op = cls(A_local, cuts, group, mode)
-        A_local.make_empty()  # the split blocks are what the product uses
+        if op.mode != "peer":
+            A_local.make_empty()  # the split blocks are what the product uses
         return op
 
     @classmethod
@@ -192,6 +253,17 @@ class DistSpMV:
     def apply(self, x_local, y_local):
         """y_local = (A x)[owned rows]; x_local / y_local are this rank's slices (device tensors, float64)."""
         ops = self.ops
+        if self.mode == "peer":
+            b = self._k % 2
+            self._k += 1
+            xb = self.x_buffers[b]
+            if x_local.data_ptr() != xb.data_ptr():
+                xb.copy_(x_local)
+            dist.all_reduce(self._flag, group=self.group)  # barrier, stream-ordered: every slice is written
+            check(lib().g4s_spmv_partitioned_device(self.A.handle, C.c_int(self.world), C.c_int(self.rank),
+                                                    self._parts[b], self._cuts_c, C.c_void_p(y_local.data_ptr()),
+                                                    _stream_ptr(torch.cuda.current_stream())))
+            return y_local
         if ops.device_type != "cuda":
             return self._apply_sync(x_local, y_local)
         main = torch.cuda.current_stream()

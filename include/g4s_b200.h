@@ -166,6 +166,18 @@ int g4s_partition_rows_i64(const long long *work_prefix, int rows, int parts, in
  * g4s_device_free) and rewrites the block's column ids to positions in that list.  g4s_gather_f64 packs
  * dst[k] = src[idx[k]].  The exchange itself (NCCL) is the caller's, see g4s_b200/dist.py. */
 int g4s_csr_split_columns(g4s_csr_t A, int c0, int c1, g4s_csr_t *diag, g4s_csr_t *off, void *stream);
+/* Fused alternative (one NVSwitch box, world <= 8): y = A x in ONE kernel, where A is the rank's row block with
+ * GLOBAL column ids and x is partitioned: x_parts[q] (host array of `world` device pointers this GPU can
+ * dereference: its own slice for q == self, CUDA-IPC-mapped peer memory otherwise) holds x[cuts[q] .. cuts[q+1]).
+ * Entries owned by other GPUs are loaded over NVLink from inside the SpMV kernel; no exchange step, no second
+ * kernel.  The caller orders the product after every rank has written its slice (a barrier). */
+int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
+                                double *y_dev, void *stream);
+/* Peer memory: cudaMalloc + CUDA IPC handle (64 bytes) / open a peer's handle / close / free. */
+int g4s_peer_alloc(size_t bytes, void **ptr_dev, unsigned char *handle64);
+int g4s_peer_open(const unsigned char *handle64, void **ptr_dev);
+int g4s_peer_close(void *ptr_dev);
+int g4s_peer_free(void *ptr_dev);
 int g4s_csr_row_map(g4s_csr_t h, const int **row_map_dev, int *full_rows);
 int g4s_csr_compact_columns(g4s_csr_t A, int **needed_cols_dev, int *n_needed, void *stream);
 int g4s_gather_f64(double *dst_dev, const double *src_dev, const int *idx_dev, long long n, void *stream);

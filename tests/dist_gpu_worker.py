@@ -29,13 +29,19 @@ def main():
         x = np.random.default_rng(7).uniform(-1, 1, A[1])
         want = oracle.spmv_csr(A[2], A[3], A[4], x)
         scale = oracle.spmv_csr_abs(A[2], A[3], A[4], x)
-        for mode in ("halo", "allgather", "auto"):
+        for mode in ("halo", "allgather", "auto", "peer"):
             op = DistSpMV.from_global(g4s_b200.CSR(A[0], A[1], A[2], A[3], A[4]), mode=mode)
             xl = torch.from_numpy(x[op.c0:op.c1].copy()).cuda()
             yl = torch.zeros(op.local_rows, dtype=torch.float64, device="cuda")
-            for _ in range(3):  # repeated application reuses the plan and the streams
-                op.apply(xl, yl)
+            for it in range(3):  # repeated application reuses the plan, the streams and both peer buffers
+                if mode == "peer" and it == 2:
+                    op.next_x().copy_(xl)  # fill the shared buffer in place
+                    op.apply(op.next_x(), yl)
+                else:
+                    op.apply(xl, yl)
             torch.cuda.synchronize()
+            if mode == "peer":
+                op.close()
             err = np.abs(yl.cpu().numpy() - want[op.c0:op.c1])
             good = bool(np.all(err <= 1e-12 * scale[op.c0:op.c1] + 1e-300))
             if not good:
@@ -53,6 +59,12 @@ def main():
     torch.cuda.synchronize()
     good = bool(np.all(np.abs(yl.cpu().numpy() - want[op.c0:op.c1]) <= 1e-12 * 52 * 2))
     ok = ok and good and op.mode == "halo"
+    op = DistSpMV.laplacian3d27(n, mode="peer")
+    yl.zero_()
+    op.apply(xl, yl)
+    torch.cuda.synchronize()
+    ok = ok and bool(np.all(np.abs(yl.cpu().numpy() - want[op.c0:op.c1]) <= 1e-12 * 52 * 2))
+    op.close()
     # ---- SpGEMM: A cut by work, B broadcast -----------------------------------------------------------------------
     A = laplacian_2d(40)
     total, work = oracle.intprod(A[2], A[3], A[2])
