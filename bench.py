@@ -233,7 +233,7 @@ def run_ours(args, rank, world):
         launches_per_step = op.launches_per_step
         parallelism = {
             "peer": "rows cut by nnz over %d GPUs; ONE fused SpMV kernel per GPU loads remote x entries over NVLink from "
-                    "CUDA-IPC peer memory; a 4-byte NCCL all-reduce per step is the barrier",
+                    "CUDA-IPC peer memory, ordered by per-rank readiness flags (release/acquire over NVLink); no collective in the step",
             "halo": "rows cut by nnz over %d GPUs; halo of x exchanged with NCCL all_to_all, overlapped with the "
                     "diagonal-block product",
             "allgather": "rows cut by nnz over %d GPUs; x assembled with NCCL all-gather, overlapped with the "

@@ -54,7 +54,8 @@ struct XParts;
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
              const XParts *parts = nullptr);
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
-                         cudaStream_t stream);
+                         const unsigned long long *flags, unsigned long long epoch, cudaStream_t stream);
+int peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, cudaStream_t stream);
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream);
 void spmv_free_plan(g4s_csr *h);
 
@@ -269,11 +270,19 @@ int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const in
 }
 
 int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
-                                double *y_dev, void *stream) {
+                                double *y_dev, const unsigned long long *ready_flags_dev, unsigned long long epoch,
+                                void *stream) {
     if (!A || !x_parts || !cuts || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_partitioned_device: null argument");
     int rc = ensure_device();
     if (rc) return rc;
-    return spmv_run_partitioned(A, world, self, x_parts, cuts, y_dev, (cudaStream_t)stream);
+    return spmv_run_partitioned(A, world, self, x_parts, cuts, y_dev, ready_flags_dev, epoch, (cudaStream_t)stream);
+}
+
+int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, void *stream) {
+    if (!flag_arrays) return fail(G4S_ERR_INVALID, "g4s_peer_signal: null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return peer_signal(flag_arrays, world, self, epoch, (cudaStream_t)stream);
 }
 
 // ---- peer memory (CUDA IPC): buffers that other ranks' kernels on the same box read over NVLink ------------------

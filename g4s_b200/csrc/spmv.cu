@@ -289,6 +289,9 @@ struct XParts {
     int world;
     int lo, hi;  // this GPU's own column range and slice
     const double *self_base;
+    // readiness flags written by the owners (flags[q] >= epoch: rank q's slice for this product is in place)
+    const unsigned long long *flags;
+    unsigned long long epoch;
 };
 __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
     if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
@@ -300,7 +303,41 @@ __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
             b = xp.base[i];
             cut = xp.cut[i];
         }
-    return __ldg(b + (c - cut));
+    return *reinterpret_cast<const volatile double *>(b + (c - cut));  // ordered after the flag acquire
+}
+
+// same lookup without the early-out, returning the address: lets the compiler issue many of them back to back
+__device__ __forceinline__ const double *x_part_ptr(const XParts &xp, int c) {
+    const double *b = xp.base[0];
+    int cut = xp.cut[0];
+#pragma unroll
+    for (int i = 1; i < MAX_PARTS; ++i) {
+        const bool ge = i < xp.world && c >= xp.cut[i];
+        b = ge ? xp.base[i] : b;
+        cut = ge ? xp.cut[i] : cut;
+    }
+    return b + (c - cut);
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// warp-collective: lane q waits until rank q has published this product's epoch.  Ten seconds without progress
+// means a peer died: trap, so that the failure is loud instead of a silent hang.
+__device__ __forceinline__ void wait_peers(const XParts &xp, int lane) {
+    if (lane < xp.world) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys_u64(xp.flags + lane) < xp.epoch) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ULL) __trap();
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
 }
 
 template <int CAP>
@@ -318,6 +355,24 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
     constexpr int PER_PASS = 32 / L;
     const int g = lane / L, sub = lane % L;
     const double *__restrict__ x = a.x;
+    if (PART) {
+        // A chunk that touches another GPU's slice: NVLink loads cost microseconds, so they are not chained into
+        // the row sums.  First every staged value is multiplied by its x entry, 32 consecutive nonzeros per step
+        // with all loads of a step batch independent (many in flight per lane); the row sums below then read
+        // finished products out of shared memory.
+        double *pv = const_cast<double *>(buf.vals);
+        const int kb = nnz0 - a0, kend = nnz1 - a0;
+        int k = kb + lane;
+        for (; k + 7 * 32 < kend; k += 8 * 32) {
+            double xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = *x_part_ptr(xp, buf.cols[k + u * 32]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pv[k + u * 32] *= xv[u];
+        }
+        for (; k < kend; k += 32) pv[k] *= *x_part_ptr(xp, buf.cols[k]);
+        __syncwarp();
+    }
     for (int base = 0; base < nloc; base += PER_PASS) {
         const int r = base + g;
         int s = 0, e = 0;
@@ -333,7 +388,7 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
         int k = s + sub - a0;
         const int ke = e - a0;
 #pragma unroll 4
-        for (; k < ke; k += L) acc = fma(buf.vals[k], PART ? load_x_part(xp, buf.cols[k]) : __ldg(x + buf.cols[k]), acc);
+        for (; k < ke; k += L) acc = PART ? acc + buf.vals[k] : fma(buf.vals[k], __ldg(x + buf.cols[k]), acc);
 #pragma unroll
         for (int o = L >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (sub == 0 && r < nloc) {
@@ -391,12 +446,14 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
     }
     __syncwarp();
 
+    bool peers_ready = !PART || xp.flags == nullptr;
     int it = 0;
     for (long long c = wglobal; c < a.nchunks; c += stride, ++it) {
         const int b = it % NBUF;
         const uint32_t parity = (it / NBUF) & 1;
         const int2 d0 = __ldg(a.desc + c), d1 = __ldg(a.desc + c + 1);
-        const int lg = a.force_lg >= 0 ? a.force_lg : (int)__ldg(a.lanes_lg + c);
+        const int code = PART ? (int)__ldg(a.part_flags + c) : (int)__ldg(a.lanes_lg + c);
+        const int lg = a.force_lg >= 0 ? a.force_lg : (code & 7);
         // loads that do not depend on the staged data go out before the wait: this chunk's row pointers
         // and the descriptor of the chunk that will reuse this ring slot
         const int nloc = d1.x > d0.x ? d1.x - d0.x : 1;
@@ -415,7 +472,11 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         const ChunkBuf<CAP> &buf = bufs[b];
         // partitioned x: only chunks that reference a remote column pay for the owner lookup; every other chunk
         // runs the plain code on the GPU's own slice (a.x = own slice rebased to global column ids)
-        const bool remote = PART && __ldg(a.part_flags + c) != 0;
+        const bool remote = PART && (code & 0x80);
+        if (PART && remote && !peers_ready) {  // only chunks that touch another GPU's slice ever wait
+            wait_peers(xp, lane);
+            peers_ready = true;
+        }
 #define G4S_CHUNK_CASE(LANES)                                                                                         \
     if (remote) chunk_rows<LANES, CAP, ACCUM, true>(buf, a, xp, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1);       \
     else chunk_rows<LANES, CAP, ACCUM, false>(buf, a, xp, (int)c, d0.x, d1.x, d0.y, d1.y, lane, rp0, rp1);             \
@@ -432,11 +493,35 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         __syncwarp();  // every lane is done reading slot b
         if (lane == 0 && next < a.nchunks) issue(b, n0.y, n1.y);
     }
+    // one warp per GPU always observes every rank's flag before the kernel ends, even when no chunk was remote:
+    // a rank can then never run two products ahead of a peer that still reads its double-buffered slice
+    if (PART && !peers_ready && blockIdx.x == 0 && warp == 0) wait_peers(xp, lane);
+}
+
+struct FlagPtrs {
+    unsigned long long *ptr[MAX_PARTS];
+};
+// thread q publishes `epoch` into rank q's flag array, slot `self` (a peer store over NVLink for q != self)
+__global__ void peer_signal_kernel(FlagPtrs f, int world, int self, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        __threadfence_system();  // everything this stream wrote before (the x slice) is visible first
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.ptr[q] + self), "l"(epoch) : "memory");
+    }
+}
+int peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, cudaStream_t stream) {
+    if (world < 1 || world > MAX_PARTS || self < 0 || self >= world) return fail(G4S_ERR_INVALID, "peer signal: 1..8 ranks");
+    FlagPtrs f;
+    for (int q = 0; q < MAX_PARTS; ++q) f.ptr[q] = q < world ? flag_arrays[q] : nullptr;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(f, world, self, epoch);
+    G4S_CHECK_LAUNCH("peer_signal_kernel");
+    return G4S_OK;
 }
 
 // one warp per chunk: does it reference a column outside [lo, hi)?
-__global__ void chunk_remote_flags_kernel(const int2 *__restrict__ desc, const int *__restrict__ colids, int nchunks,
-                                          int lo, int hi, unsigned char *__restrict__ flags) {
+__global__ void chunk_remote_flags_kernel(const int2 *__restrict__ desc, const int *__restrict__ colids,
+                                          const unsigned char *__restrict__ lanes_lg, int nchunks, int lo, int hi,
+                                          unsigned char *__restrict__ flags) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= nchunks) return;
     const int s = desc[c].y, e = desc[c + 1].y;
@@ -446,7 +531,7 @@ __global__ void chunk_remote_flags_kernel(const int2 *__restrict__ desc, const i
         any |= (col < lo || col >= hi);
     }
     any = __any_sync(0xffffffffu, any);
-    if (lane == 0) flags[c] = any ? 1 : 0;
+    if (lane == 0) flags[c] = lanes_lg[c] | (any ? 0x80 : 0);  // one byte per chunk: lanes (low bits) + remote (bit 7)
 }
 
 // y[row] += carries of the row's non-final pieces, in piece order
@@ -501,6 +586,8 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     none.world = 0;
     none.lo = none.hi = 0;
     none.self_base = nullptr;
+    none.flags = nullptr;
+    none.epoch = 0;
     if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
     else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
     else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
@@ -617,7 +704,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
 }
 
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
-                         cudaStream_t stream) {
+                         const unsigned long long *flags, unsigned long long epoch, cudaStream_t stream) {
     if (world < 1 || world > MAX_PARTS || self < 0 || self >= world)
         return fail(G4S_ERR_INVALID, "partitioned SpMV supports 1..8 parts (one NVSwitch box)");
     XParts xp;
@@ -627,6 +714,8 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     xp.lo = cuts[self];
     xp.hi = cuts[self + 1];
     xp.self_base = x_parts[self];
+    xp.flags = flags;
+    xp.epoch = epoch;
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     SpmvPlan &p = h->plan;
@@ -634,7 +723,7 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         if (!p.part_flags) G4S_CUDA(cudaMalloc(&p.part_flags, (size_t)p.nchunks + 1));
         if (p.nchunks) {
             chunk_remote_flags_kernel<<<(int)(((long long)p.nchunks * 32 + 255) / 256), 256, 0, stream>>>(
-                p.desc, h->colids, p.nchunks, xp.lo, xp.hi, p.part_flags);
+                p.desc, h->colids, p.lanes_lg, p.nchunks, xp.lo, xp.hi, p.part_flags);
             G4S_CHECK_LAUNCH("chunk_remote_flags_kernel");
         }
         p.part_lo = xp.lo;

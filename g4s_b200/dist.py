@@ -11,9 +11,11 @@ DIAGONAL block (columns it owns) and the row-compressed OFF-DIAGONAL block.  Eve
 
 "peer" mode (one NVSwitch box, <= 8 GPUs) removes the exchange altogether: every rank keeps its x slice in a
 CUDA-IPC-shared buffer, the row block is NOT split, and ONE SpMV kernel loads the entries owned by other GPUs
-straight from their memory over NVLink while it streams its own matrix (g4s_spmv_partitioned_device).  A tiny
-all-reduce per product is the barrier that orders it after every rank has written its slice; x is double-buffered
-so that the barrier of product k+1 also covers "everyone is done reading the buffer of product k-1".
+straight from their memory over NVLink while it streams its own matrix (g4s_spmv_partitioned_device).  There is no
+collective in the product: after writing its slice a rank stores the product's epoch into every peer's flag array
+(g4s_peer_signal, a release store over NVLink), and only the chunks of the SpMV kernel that touch another GPU's
+slice wait for the owners' flags; the rest of the matrix streams meanwhile.  x is double-buffered and every kernel
+observes all flags before it ends, so a rank can never overwrite a slice that a slower peer is still reading.
 
 "halo" mode moves only the x entries that are referenced (for a stencil: two planes per neighbour instead of the
 whole vector); "allgather" mode is the plain NCCL all-gather of x named in BASELINE.json's north_star and is the
@@ -180,15 +182,19 @@ class DistSpMV:
         self.mode = "peer"
         self.A = A_local
         self._own, mine = [], []
-        for _ in range(2):
+        for b in range(3):  # two x buffers and the flag array
             ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
-            check(L.g4s_peer_alloc(C.c_size_t(8 * max(self.local_rows, 1)), C.byref(ptr), h))
+            nbytes = 8 * max(self.local_rows, 1) if b < 2 else 8 * 8
+            check(L.g4s_peer_alloc(C.c_size_t(nbytes), C.byref(ptr), h))
             self._own.append(ptr.value)
             mine.append(bytes(h))
+        self._flags = torch.as_tensor(_DevArray(self._own[2], 8, "<i8"), device=dev)
+        self._flags.zero_()
+        torch.cuda.synchronize()
         every = [None] * self.world
         dist.all_gather_object(every, mine, group=self.group)
         self._opened, self._parts = [], []
-        for b in range(2):
+        for b in range(3):
             arr = (C.c_void_p * self.world)()
             for q in range(self.world):
                 if q == self.rank:
@@ -202,9 +208,9 @@ class DistSpMV:
         self.x_buffers = [torch.as_tensor(_DevArray(self._own[b], max(self.local_rows, 1), "<f8"), device=dev)[:self.local_rows]
                           for b in range(2)]
         self._cuts_c = (C.c_int * (self.world + 1))(*self.cuts)
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._flag_arrays = self._parts.pop()
         self._k = 0
-        self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 1
+        self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 2
         dist.barrier(group=self.group)
 
     def next_x(self):
@@ -259,10 +265,12 @@ class DistSpMV:
             xb = self.x_buffers[b]
             if x_local.data_ptr() != xb.data_ptr():
                 xb.copy_(x_local)
-            dist.all_reduce(self._flag, group=self.group)  # barrier, stream-ordered: every slice is written
+            st = _stream_ptr(torch.cuda.current_stream())
+            epoch = C.c_ulonglong(self._k)  # products are numbered from 1; flags start at 0
+            check(lib().g4s_peer_signal(self._flag_arrays, C.c_int(self.world), C.c_int(self.rank), epoch, st))
             check(lib().g4s_spmv_partitioned_device(self.A.handle, C.c_int(self.world), C.c_int(self.rank),
                                                     self._parts[b], self._cuts_c, C.c_void_p(y_local.data_ptr()),
-                                                    _stream_ptr(torch.cuda.current_stream())))
+                                                    C.c_void_p(self._own[2]), epoch, st))
             return y_local
         if ops.device_type != "cuda":
             return self._apply_sync(x_local, y_local)

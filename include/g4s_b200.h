@@ -170,9 +170,17 @@ int g4s_csr_split_columns(g4s_csr_t A, int c0, int c1, g4s_csr_t *diag, g4s_csr_
  * GLOBAL column ids and x is partitioned: x_parts[q] (host array of `world` device pointers this GPU can
  * dereference: its own slice for q == self, CUDA-IPC-mapped peer memory otherwise) holds x[cuts[q] .. cuts[q+1]).
  * Entries owned by other GPUs are loaded over NVLink from inside the SpMV kernel; no exchange step, no second
- * kernel.  The caller orders the product after every rank has written its slice (a barrier). */
+ * kernel.  Ordering against the owners' writes is either the caller's (ready_flags_dev == NULL: run a barrier first)
+ * or in-kernel: ready_flags_dev points at this rank's array of `world` 64-bit flags in peer-shared memory, into
+ * which rank q stores `epoch` with g4s_peer_signal once its slice for this product is written; only the chunks
+ * that touch another GPU's slice wait (acquire) for flags >= epoch, the rest of the matrix streams meanwhile. */
 int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
-                                double *y_dev, void *stream);
+                                double *y_dev, const unsigned long long *ready_flags_dev, unsigned long long epoch,
+                                void *stream);
+/* flag_arrays[q] = rank q's flag array (own or IPC-mapped).  Stream-ordered after the writes of the x slice:
+ * stores `epoch` into slot `self` of every rank's array (release, system scope). */
+int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch,
+                    void *stream);
 /* Peer memory: cudaMalloc + CUDA IPC handle (64 bytes) / open a peer's handle / close / free. */
 int g4s_peer_alloc(size_t bytes, void **ptr_dev, unsigned char *handle64);
 int g4s_peer_open(const unsigned char *handle64, void **ptr_dev);
