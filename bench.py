@@ -316,8 +316,9 @@ def run_ours(args, rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "note": "matrix resident on the GPU (g4s_csr handle created once, as MKL's create_csr in the "
-                        "reference's mkl()); x uploaded from pinned host memory and y downloaded every step"},
+                "note": "g4s_spmv_host: matrix resident on the GPU (g4s_csr handle created once, as MKL's create_csr "
+                        "in the reference's mkl()); every step uploads x from pinned host memory and downloads y; "
+                        "the call pipelines upload / row-block products / download on three streams"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "spmv_chunk_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic},

@@ -52,7 +52,9 @@ int sm_count() {
 
 struct XParts;
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
-             const XParts *parts = nullptr);
+             const XParts *parts = nullptr, int chunk_begin = 0, int chunk_end = -1);
+int spmv_host_pipelined(g4s_csr *h, const double *x, double *y);
+void spmv_free_host_pipe(g4s_csr *h);
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
                          const unsigned long long *flags, unsigned long long epoch, cudaStream_t stream);
 int peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, cudaStream_t stream);
@@ -210,6 +212,7 @@ int g4s_csr_create_device(g4s_csr_t *out, int rows, int cols, const int *rowptr_
 
 int g4s_csr_destroy(g4s_csr_t h) {
     if (!h) return G4S_OK;
+    spmv_free_host_pipe(h);
     spmv_free_plan(h);
     if (h->owns && h->pooled) {
         cudaDeviceSynchronize();  // cudaFree's implicit guarantee: nothing in flight still uses the arrays
@@ -319,14 +322,8 @@ int g4s_spmv_host(g4s_csr_t A, const double *x, double *y) {
     if (!A || (!x && A->cols) || (!y && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_host: null argument");
     int rc = ensure_device();
     if (rc) return rc;
-    if (!A->x_dev) G4S_CUDA(cudaMalloc(&A->x_dev, sizeof(double) * (size_t)std::max(A->cols, 1)));
-    if (!A->y_dev) G4S_CUDA(cudaMalloc(&A->y_dev, sizeof(double) * (size_t)std::max(A->rows, 1)));
-    G4S_CUDA(cudaMemcpyAsync(A->x_dev, x, sizeof(double) * (size_t)A->cols, cudaMemcpyHostToDevice, 0));
-    rc = spmv_run(A, A->x_dev, A->y_dev, nullptr, false, 0);
-    if (rc) return rc;
-    G4S_CUDA(cudaMemcpyAsync(y, A->y_dev, sizeof(double) * (size_t)A->rows, cudaMemcpyDeviceToHost, 0));
-    G4S_CUDA(cudaStreamSynchronize(0));
-    return G4S_OK;
+    if (A->rows == 0) return G4S_OK;
+    return spmv_host_pipelined(A, x, y);
 }
 
 int g4s_spmv_csr_f64(int rows, int cols, const int *rowptr, const int *colids, const double *values,

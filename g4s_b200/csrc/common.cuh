@@ -51,6 +51,8 @@ struct SpmvPlan {
     int variant = 0;                    // tuning override, 0 = default kernel shape
 };
 
+struct HostPipe;  // spmv.cu: streams / events / row blocks of the pipelined host-pointer product
+
 }  // namespace g4s
 
 struct g4s_csr {
@@ -68,6 +70,7 @@ struct g4s_csr {
     int full_rows = 0;
     // scratch for the host-pointer entry points
     double *x_dev = nullptr, *y_dev = nullptr;
+    g4s::HostPipe *host_pipe = nullptr;
 };
 
 namespace g4s {

@@ -274,7 +274,8 @@ struct SpmvArgs {
     const int *row_map;  // optional: local row r is y[row_map[r]] (row-compressed off-diagonal blocks)
     int rows;
     long long nnz;
-    int nchunks;
+    int nchunks;       // one past the last chunk this launch processes
+    int chunk_begin;   // first chunk this launch processes (row-block launches of the pipelined host path)
     int force_lg;  // -1: use the inspector's choice
     const unsigned char *part_flags;  // partitioned x: 1 where a chunk references a column another GPU owns
 };
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         }
     };
 
-    const int wglobal = blockIdx.x * WARPS + warp;
+    const int wglobal = a.chunk_begin + blockIdx.x * WARPS + warp;
     const int stride = gridDim.x * WARPS;
     if (lane == 0) {
         policy = policy_evict_first();
@@ -579,7 +580,7 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
         G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    long long want = ((long long)args.nchunks + WARPS - 1) / WARPS;
+    long long want = ((long long)(args.nchunks - args.chunk_begin) + WARPS - 1) / WARPS;
     int grid = (int)std::min<long long>(want, (long long)sm_count() * ctas_per_sm);
     if (grid < 1) grid = 1;
     XParts none;
@@ -652,7 +653,7 @@ void spmv_free_plan(g4s_csr *h) {
 }
 
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
-             const XParts *parts) {
+             const XParts *parts, int chunk_begin, int chunk_end) {
     if (h->rows == 0) return G4S_OK;
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
@@ -675,7 +676,8 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     a.row_map = row_map;
     a.rows = h->rows;
     a.nnz = h->nnz;
-    a.nchunks = p.nchunks;
+    a.nchunks = chunk_end >= 0 ? chunk_end : p.nchunks;
+    a.chunk_begin = chunk_begin;
     a.force_lg = -1;
     a.part_flags = nullptr;
     a.part_flags = parts ? p.part_flags : nullptr;
@@ -696,7 +698,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
         default: rc = launch_chunk_kernel<SPMV_CAP, 1, 9>(a, accum, 2, stream, parts); break;
     }
     if (rc) return rc;
-    if (p.n_long > 0) {
+    if (p.n_long > 0 && chunk_end < 0) {  // row-block launches leave the fix-up to the caller
         spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, stream>>>(p.long_rows, p.n_long, p.carry, row_map, y);
         G4S_CHECK_LAUNCH("spmv_long_fixup_kernel");
     }
@@ -730,7 +732,129 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         p.part_hi = xp.hi;
     }
     // the plain path indexes x by global column id: rebase the own slice (never dereferenced outside [lo, hi))
-    return spmv_run(h, x_parts[self] - xp.lo, y, nullptr, false, stream, &xp);
+    return spmv_run(h, x_parts[self] - xp.lo, y, nullptr, false, stream, &xp, 0, -1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Host-pointer product, pipelined: y = A x with x and y in (pinned) host memory.
+// The chunk list is cut into NB row blocks of equal chunk count; block b needs x[0 .. colmax_b] to have arrived.
+// For banded matrices colmax grows with b, so the upload of x (copy stream), the products of the blocks whose
+// x range is complete (compute stream) and the download of finished y blocks (second copy stream) all overlap,
+// and PCIe runs in both directions at once.  A matrix whose first block already references the end of x
+// degenerates to upload-all / compute / download, which is what a non-pipelined call does.
+// ------------------------------------------------------------------------------------------------------
+__global__ void block_colmax_kernel(const int2 *__restrict__ desc, const int *__restrict__ colids, int nchunks,
+                                    int chunks_per_block, int *__restrict__ colmax) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    int m = -1;
+    for (int k = desc[c].y + lane; k < desc[c + 1].y; k += 32) m = max(m, __ldg(colids + k));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m >= 0) atomicMax(&colmax[c / chunks_per_block], m);
+}
+
+struct HostPipe {
+    int nb = 0, chunks_per_block = 0;
+    std::vector<int> colmax, row_end;  // per block: highest column referenced (running max), one past its last row
+    cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_comp;
+    cudaEvent_t ev_start = nullptr;
+};
+
+int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
+    int rc = spmv_build_plan(h, 0);
+    if (rc) return rc;
+    const SpmvPlan &p = h->plan;
+    HostPipe *&hp = h->host_pipe;
+    if (!hp) {
+        hp = new HostPipe();
+        hp->nb = std::max(1, std::min(32, p.nchunks / 4096));
+        hp->chunks_per_block = (p.nchunks + hp->nb - 1) / hp->nb;
+        hp->nb = (p.nchunks + hp->chunks_per_block - 1) / hp->chunks_per_block;
+        int *dmax = nullptr;
+        G4S_CUDA(cudaMalloc(&dmax, sizeof(int) * hp->nb));
+        G4S_CUDA(cudaMemset(dmax, 0xff, sizeof(int) * hp->nb));
+        block_colmax_kernel<<<(int)(((long long)p.nchunks * 32 + 255) / 256), 256>>>(p.desc, h->colids, p.nchunks,
+                                                                                     hp->chunks_per_block, dmax);
+        G4S_CHECK_LAUNCH("block_colmax_kernel");
+        hp->colmax.resize(hp->nb);
+        G4S_CUDA(cudaMemcpy(hp->colmax.data(), dmax, sizeof(int) * hp->nb, cudaMemcpyDeviceToHost));
+        cudaFree(dmax);
+        std::vector<int2> hdesc(hp->nb + 1);
+        for (int b = 0; b <= hp->nb; ++b) {
+            const int c = std::min(b * hp->chunks_per_block, p.nchunks);
+            G4S_CUDA(cudaMemcpy(&hdesc[b], p.desc + c, sizeof(int2), cudaMemcpyDeviceToHost));
+        }
+        hp->row_end.resize(hp->nb);
+        for (int b = 0; b < hp->nb; ++b) {
+            hp->row_end[b] = hdesc[b + 1].x;  // first row of the next block (a long row cut here is handled below)
+            if (b) hp->colmax[b] = std::max(hp->colmax[b], hp->colmax[b - 1]);
+        }
+        hp->row_end[hp->nb - 1] = h->rows;
+        G4S_CUDA(cudaStreamCreateWithFlags(&hp->up, cudaStreamNonBlocking));
+        G4S_CUDA(cudaStreamCreateWithFlags(&hp->comp, cudaStreamNonBlocking));
+        G4S_CUDA(cudaStreamCreateWithFlags(&hp->down, cudaStreamNonBlocking));
+        hp->ev_up.resize(hp->nb);
+        hp->ev_comp.resize(hp->nb);
+        for (int b = 0; b < hp->nb; ++b) {
+            G4S_CUDA(cudaEventCreateWithFlags(&hp->ev_up[b], cudaEventDisableTiming));
+            G4S_CUDA(cudaEventCreateWithFlags(&hp->ev_comp[b], cudaEventDisableTiming));
+        }
+        G4S_CUDA(cudaEventCreateWithFlags(&hp->ev_start, cudaEventDisableTiming));
+    }
+    if (!h->x_dev) G4S_CUDA(cudaMalloc(&h->x_dev, sizeof(double) * (size_t)std::max(h->cols, 1)));
+    if (!h->y_dev) G4S_CUDA(cudaMalloc(&h->y_dev, sizeof(double) * (size_t)std::max(h->rows, 1)));
+    // order after whatever the caller queued on the default stream
+    G4S_CUDA(cudaEventRecord(hp->ev_start, 0));
+    G4S_CUDA(cudaStreamWaitEvent(hp->up, hp->ev_start, 0));
+    G4S_CUDA(cudaStreamWaitEvent(hp->comp, hp->ev_start, 0));
+    G4S_CUDA(cudaStreamWaitEvent(hp->down, hp->ev_start, 0));
+    const bool defer_download = p.n_long > 0;  // the long-row fix-up touches y after every block has run
+    long long uploaded = 0;
+    int row0 = 0;
+    for (int b = 0; b < hp->nb; ++b) {
+        const long long need = std::min<long long>((long long)hp->colmax[b] + 1, h->cols);
+        if (need > uploaded) {
+            G4S_CUDA(cudaMemcpyAsync(h->x_dev + uploaded, x + uploaded, sizeof(double) * (size_t)(need - uploaded),
+                                     cudaMemcpyHostToDevice, hp->up));
+            uploaded = need;
+        }
+        G4S_CUDA(cudaEventRecord(hp->ev_up[b], hp->up));
+        G4S_CUDA(cudaStreamWaitEvent(hp->comp, hp->ev_up[b], 0));
+        const int c0 = b * hp->chunks_per_block, c1 = std::min(c0 + hp->chunks_per_block, p.nchunks);
+        rc = spmv_run(h, h->x_dev, h->y_dev, nullptr, false, hp->comp, nullptr, c0, c1);
+        if (rc) return rc;
+        G4S_CUDA(cudaEventRecord(hp->ev_comp[b], hp->comp));
+        if (!defer_download && hp->row_end[b] > row0) {
+            G4S_CUDA(cudaStreamWaitEvent(hp->down, hp->ev_comp[b], 0));
+            G4S_CUDA(cudaMemcpyAsync(y + row0, h->y_dev + row0, sizeof(double) * (size_t)(hp->row_end[b] - row0),
+                                     cudaMemcpyDeviceToHost, hp->down));
+            row0 = hp->row_end[b];
+        }
+    }
+    if (defer_download) {
+        spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, hp->comp>>>(p.long_rows, p.n_long, p.carry, nullptr, h->y_dev);
+        G4S_CHECK_LAUNCH("spmv_long_fixup_kernel");
+        G4S_CUDA(cudaMemcpyAsync(y, h->y_dev, sizeof(double) * (size_t)h->rows, cudaMemcpyDeviceToHost, hp->comp));
+        G4S_CUDA(cudaStreamSynchronize(hp->comp));
+    }
+    G4S_CUDA(cudaStreamSynchronize(hp->down));
+    G4S_CUDA(cudaStreamSynchronize(hp->comp));
+    return G4S_OK;
+}
+
+void spmv_free_host_pipe(g4s_csr *h) {
+    HostPipe *hp = h->host_pipe;
+    if (!hp) return;
+    for (auto e : hp->ev_up) cudaEventDestroy(e);
+    for (auto e : hp->ev_comp) cudaEventDestroy(e);
+    if (hp->ev_start) cudaEventDestroy(hp->ev_start);
+    if (hp->up) cudaStreamDestroy(hp->up);
+    if (hp->comp) cudaStreamDestroy(hp->comp);
+    if (hp->down) cudaStreamDestroy(hp->down);
+    delete hp;
+    h->host_pipe = nullptr;
 }
 
 }  // namespace g4s
