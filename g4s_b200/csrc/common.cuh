@@ -62,6 +62,7 @@ struct g4s_csr {
     int *colids = nullptr;
     double *values = nullptr;
     bool owns = false;
+    int sorted_cols = -1;  // -1 unknown, 1 every row's column ids strictly ascending, 0 not (SpGEMM merge class)
     bool pooled = false;  // arrays came from cudaMallocAsync (stream-ordered pool) rather than cudaMalloc
     g4s::SpmvPlan plan;
     // row-compressed blocks (off-diagonal part of a multi-GPU row block): local row r is row row_map[r] of a

@@ -10,11 +10,13 @@
 // Where the reference gives each OpenMP thread one reusable table and walks rows one after another, the GPU
 // gives every ROW its own table, sized by the row's intermediate-product count w = min(work, cols):
 //   class 0  w == 0        nothing to do (row is empty)
-//   class 1  w <= 32       4 lanes per row, 32-slot table in shared memory (64 rows per CTA)
-//   class 2  w <= 256      one warp per row, 512 slots
-//   class 3  w <= 2048     one 256-thread CTA per row, 4096 slots
-//   class 4  w <= 8192     one 1024-thread CTA per row, 8192 slots
-//   class 5  larger        one CTA per row, power-of-two table in global memory (persistent CTAs own a slab)
+//   class 1  <= 8 entries in A's row, <= 64 products, B's rows sorted: one thread per row, k-way MERGE in registers
+//   class 2  w <= 32       one thread per row, private 32-slot table in shared memory (bank-interleaved)
+//   class 3  w <= 256      one warp per row, 512 slots
+//   class 4  w <= 2048     one 256-thread CTA per row, 4096 slots
+//   class 5  w <= 8192     one 1024-thread CTA per row, 8192 slots
+//   class 6  larger        one CTA per row, power-of-two table in global memory (persistent CTAs own a slab)
+// Classes 1 and 2 keep the reference's sequential accumulation order: their VALUES are bit-identical to it.
 // Hash = (key * 107) & (size-1) with linear probing, empty = -1, exactly the reference's function
 // (hash_mult.h:23, :89-101); insertion uses atomicCAS on the key and atomicAdd(double) on the value, so the
 // accumulation order inside a row differs from the reference's sequential order (values agree to rounding;
@@ -34,23 +36,27 @@ int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, lo
                        cudaStream_t stream);
 int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz);
 
-constexpr int NCLASS = 6;
+constexpr int NCLASS = 7;
+constexpr int MERGE_MAX_A = 8;    // class 1: rows of A with at most this many entries ...
+constexpr int MERGE_MAX_W = 64;   // ... and at most this many intermediate products, when B's rows are sorted
 constexpr int HASH_MULT = 107;  // mm/inc/hash_mult.h:23
 
-__host__ __device__ inline int work_class(int work, int cols) {
+__host__ __device__ inline int work_class(int work, int cols, int alen, bool b_sorted) {
     const int w = work < cols ? work : cols;
     if (w == 0) return 0;
-    if (w <= 32) return 1;
-    if (w <= 256) return 2;
-    if (w <= 2048) return 3;
-    if (w <= 8192) return 4;
-    return 5;
+    if (b_sorted && alen <= MERGE_MAX_A && work <= MERGE_MAX_W) return 1;
+    if (w <= 32) return 2;
+    if (w <= 256) return 3;
+    if (w <= 2048) return 4;
+    if (w <= 8192) return 5;
+    return 6;
 }
 
 // ---- per-row work (BIN::set_intprod_num) + class histogram ----------------------------------------------
 __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restrict__ acol,
                                 const int *__restrict__ brpt, int M, int cols, int *__restrict__ row_work,
-                                unsigned long long *__restrict__ total, int *__restrict__ class_count) {
+                                unsigned long long *__restrict__ total, int *__restrict__ class_count,
+                                unsigned char *__restrict__ row_class, bool b_sorted) {
     // class_count: [NCLASS] histogram, then [NCLASS] cursors (unused here), then [1] max work
     __shared__ int hist[NCLASS];
     __shared__ unsigned long long bsum;
@@ -71,7 +77,9 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
         const int wi = w > 2147483647LL ? 2147483647 : (int)w;
         if (row_work) row_work[i] = wi;
         if (class_count) {
-            atomicAdd(&hist[work_class(wi, cols)], 1);
+            const int cls = work_class(wi, cols, __ldg(arpt + i + 1) - __ldg(arpt + i), b_sorted);
+            row_class[i] = (unsigned char)cls;
+            atomicAdd(&hist[cls], 1);
             if (wi) atomicMax(&bmax, wi);
         }
     }
@@ -86,13 +94,13 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
 }
 
 // rows of each class, ascending inside a block of 256 rows; blocks reserve their ranges with one atomic per class
-__global__ void bin_fill_kernel(const int *__restrict__ row_work, int M, int cols, int *__restrict__ cursor,
+__global__ void bin_fill_kernel(const unsigned char *__restrict__ row_class, int M, int *__restrict__ cursor,
                                 int *__restrict__ perm, int *__restrict__ row_nnz) {
     __shared__ int wcount[NCLASS][8];
     __shared__ int base[NCLASS];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c = i < M ? work_class(row_work[i], cols) : -1;
+    const int c = i < M ? (int)row_class[i] : -1;
     if (c == 0) row_nnz[i] = 0;
     int my_rank = 0;
 #pragma unroll
@@ -378,6 +386,76 @@ __global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const Spgemm
     }
 }
 
+// class 1: ONE THREAD PER ROW, NO TABLE.  When B's rows are sorted, a row of A with at most 8 entries is a k-way
+// merge of at most 8 sorted rows of B: the thread keeps one cursor per list in registers, repeatedly takes the
+// smallest head column and folds every list that carries it, in list order — which is the reference's
+// accumulation order (j ascending over A's row, one entry of B's row per column; hash_mult.h:579-600), so the
+// values are bit-identical to HashSpGEMM<false,true> and the columns come out sorted with no sort at all.
+template <bool NUMERIC>
+__global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
+                                                               int nlist) {
+    constexpr int K = MERGE_MAX_A;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nlist;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int row = list ? __ldg(list + idx) : (int)idx;
+        const int as = __ldg(a.arpt + row), na = __ldg(a.arpt + row + 1) - as;
+        int pos[K], end[K], head[K];
+        double av[K];
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            pos[u] = end[u] = 0;
+            head[u] = 0x7fffffff;
+            av[u] = 0.0;
+            if (u < na) {
+                const int k = __ldg(a.acol + as + u);
+                if (NUMERIC) av[u] = __ldg(a.aval + as + u);
+                pos[u] = __ldg(a.brpt + k);
+                end[u] = __ldg(a.brpt + k + 1);
+                if (pos[u] < end[u]) head[u] = __ldg(a.bcol + pos[u]);
+            }
+        }
+        int n = 0;
+        const int out = NUMERIC ? __ldg(a.crpt + row) : 0;
+        for (;;) {
+            int m = head[0];
+#pragma unroll
+            for (int u = 1; u < K; ++u) m = min(m, head[u]);
+            if (m == 0x7fffffff) break;
+            double v = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int u = 0; u < K; ++u) {
+                if (head[u] == m) {
+                    if (NUMERIC) {
+                        const double prod = __dmul_rn(av[u], __ldg(a.bval + pos[u]));
+                        v = first ? prod : __dadd_rn(prod, v);
+                        first = false;
+                    }
+                    ++pos[u];
+                    head[u] = pos[u] < end[u] ? __ldg(a.bcol + pos[u]) : 0x7fffffff;
+                }
+            }
+            if (NUMERIC) {
+                a.ccol[out + n] = m;
+                a.cval[out + n] = v;
+            }
+            ++n;
+        }
+        if (!NUMERIC) a.row_nnz[row] = n;
+    }
+}
+
+// strictly ascending column ids inside every row? (checked once per matrix, cached in the handle)
+__global__ void rows_sorted_kernel(const int *__restrict__ rowptr, const int *__restrict__ colids, int rows,
+                                   int *__restrict__ unsorted) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int s = rowptr[warp], e = rowptr[warp + 1];
+    int bad = 0;
+    for (int k = s + 1 + lane; k < e; k += 32) bad |= __ldg(colids + k) <= __ldg(colids + k - 1);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *unsorted = 1;
+}
+
 // class 5: tables in global memory.  Persistent CTAs; CTA b owns slab b (slab_slots entries) and re-initialises
 // only the power-of-two prefix the current row needs.
 template <bool NUMERIC>
@@ -523,16 +601,22 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
                      long long slab_slots, int slab_ctas, cudaStream_t stream) {
     int rc;
     auto list = [&](int c) -> const int * { return b.identity ? nullptr : b.perm + b.offset[c]; };
-    if ((rc = launch_thread_row<32, 128>(a, list(1), b.count[1], numeric, stream))) return rc;
-    if ((rc = launch_smem<32, 512, 256, 256>(a, list(2), b.count[2], numeric, stream))) return rc;
-    if ((rc = launch_smem<256, 4096, 2048, 256>(a, list(3), b.count[3], numeric, stream))) return rc;
-    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, list(4), b.count[4], numeric, stream))) return rc;
-    if (b.count[5]) {
+    if (b.count[1]) {
+        const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
+        if (numeric) spgemm_merge_row_kernel<true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else spgemm_merge_row_kernel<false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
+    }
+    if ((rc = launch_thread_row<32, 128>(a, list(2), b.count[2], numeric, stream))) return rc;
+    if ((rc = launch_smem<32, 512, 256, 256>(a, list(3), b.count[3], numeric, stream))) return rc;
+    if ((rc = launch_smem<256, 4096, 2048, 256>(a, list(4), b.count[4], numeric, stream))) return rc;
+    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, list(5), b.count[5], numeric, stream))) return rc;
+    if (b.count[6]) {
         if (numeric)
-            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(5), b.count[5], b.row_work,
+            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
                                                                       slab_keys, slab_vals, slab_slots);
         else
-            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, list(5), b.count[5], b.row_work,
+            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
                                                                        slab_keys, slab_vals, slab_slots);
         G4S_CHECK_LAUNCH("spgemm_global_kernel");
     }
@@ -545,6 +629,7 @@ struct Workspace {
     int device = -1;
     size_t rows_cap = 0;
     int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
+    unsigned char *row_class = nullptr;
     unsigned long long *dtotal = nullptr;
     int *hcount = nullptr;  // pinned
     unsigned long long *htotal = nullptr;
@@ -567,10 +652,12 @@ struct Workspace {
             if (row_work) cudaFree(row_work);
             if (perm) cudaFree(perm);
             if (row_nnz) cudaFree(row_nnz);
+            if (row_class) cudaFree(row_class);
             rows_cap = (size_t)M + 1;
             G4S_CUDA(cudaMalloc(&row_work, sizeof(int) * rows_cap));
             G4S_CUDA(cudaMalloc(&perm, sizeof(int) * rows_cap));
             G4S_CUDA(cudaMalloc(&row_nnz, sizeof(int) * rows_cap));
+            G4S_CUDA(cudaMalloc(&row_class, rows_cap));
         }
         return G4S_OK;
     }
@@ -595,8 +682,21 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     G4S_CUDA(cudaMemsetAsync(ws.dtotal, 0, sizeof(unsigned long long), stream));
     const int threads = 256;
     const int blocks = (M + threads - 1) / threads;
+    if (B->sorted_cols < 0) {  // once per matrix: are B's rows sorted? (decides whether class 1 may merge)
+        G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int), stream));
+        if (B->rows > 0) {
+            rows_sorted_kernel<<<(int)(((long long)B->rows * 32 + 255) / 256), 256, 0, stream>>>(B->rowptr, B->colids,
+                                                                                              B->rows, dcount);
+            G4S_CHECK_LAUNCH("rows_sorted_kernel");
+        }
+        G4S_CUDA(cudaMemcpyAsync(ws.hcount, dcount, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        G4S_CUDA(cudaStreamSynchronize(stream));
+        B->sorted_cols = ws.hcount[0] ? 0 : 1;
+        G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int), stream));
+    }
     if (M > 0) {
-        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, ws.dtotal, dcount);
+        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, ws.dtotal, dcount,
+                                                       ws.row_class, B->sorted_cols == 1);
         G4S_CHECK_LAUNCH("row_work_kernel");
     }
     G4S_CUDA(cudaMemcpyAsync(ws.hcount, dcount, sizeof(int) * (2 * NCLASS + 1), cudaMemcpyDeviceToHost, stream));
@@ -618,7 +718,7 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     }
     if (M > 0 && !b.identity) {
         G4S_CUDA(cudaMemcpyAsync(dcount + NCLASS, cur, sizeof(cur), cudaMemcpyHostToDevice, stream));
-        bin_fill_kernel<<<blocks, threads, 0, stream>>>(b.row_work, M, N, dcount + NCLASS, b.perm, row_nnz);
+        bin_fill_kernel<<<blocks, threads, 0, stream>>>(ws.row_class, M, dcount + NCLASS, b.perm, row_nnz);
         G4S_CHECK_LAUNCH("bin_fill_kernel");
     }
     G4S_CUDA(cudaEventRecord(ws.ev[1], stream));
@@ -634,13 +734,13 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     double *slab_vals = nullptr;
     long long slab_slots = 0;
     int slab_ctas = 0;
-    if (b.count[5]) {
+    if (b.count[6]) {
         const long long w = std::min<long long>(b.max_work, N);
         slab_slots = 16384;
         while (slab_slots < 2 * w) slab_slots <<= 1;
         const long long budget = 2LL << 30;  // bytes of scratch
         slab_ctas = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 2, budget / (slab_slots * 12)));
-        slab_ctas = std::min(slab_ctas, b.count[5]);
+        slab_ctas = std::min(slab_ctas, b.count[6]);
         G4S_CUDA(cudaMallocAsync(&slab_keys, sizeof(int) * (size_t)slab_slots * slab_ctas, stream));
         G4S_CUDA(cudaMallocAsync(&slab_vals, sizeof(double) * (size_t)slab_slots * slab_ctas, stream));
     }
@@ -737,7 +837,7 @@ int g4s_compute_flop_device(g4s_csr_t A, g4s_csr_t B, long long *total, int *row
     G4S_CUDA(cudaMemsetAsync(dtotal, 0, sizeof(unsigned long long), stream));
     if (A->rows > 0) {
         row_work_kernel<<<(A->rows + 255) / 256, 256, 0, stream>>>(A->rowptr, A->colids, B->rowptr, A->rows, B->cols,
-                                                                  row_work_dev, dtotal, nullptr);
+                                                                  row_work_dev, dtotal, nullptr, nullptr, false);
         G4S_CHECK_LAUNCH("row_work_kernel");
     }
     unsigned long long h = 0;

@@ -49,8 +49,23 @@ def banded(rows, half_width, seed):
     return to_tuple(sp.diags(diags, list(range(-half_width, half_width + 1)), shape=(rows, rows)))
 
 
+def shuffled(t, seed):
+    """Permute the stored order inside every row (the reference's CSR::shuffleIds idea, mm/inc/CSR.h:671-689): the
+    hash algorithm does not need sorted inputs, and unsorted B rows keep the GPU off its merge fast path."""
+    rng = np.random.default_rng(seed)
+    rp, ci, va = t[2], t[3].copy(), t[4].copy()
+    for r in range(t[0]):
+        s, e = rp[r], rp[r + 1]
+        perm = rng.permutation(e - s)
+        ci[s:e], va[s:e] = ci[s:e][perm], va[s:e][perm]
+    return (t[0], t[1], rp, ci, va)
+
+
 CASES = {
-    "tridiag3": lambda: (tridiag3(),) * 2,                                             # class 1
+    "tridiag3": lambda: (tridiag3(),) * 2,                                             # class 1 (merge)
+    "lap2d_40_shuffled": lambda: (shuffled(laplacian_2d(40), 1), shuffled(laplacian_2d(40), 2)),  # class 2 (thread hash)
+    "rand_rect_shuffled": lambda: (shuffled(random_csr(300, 200, 0.04, 2, empty_rows=True), 3),
+                                   shuffled(random_csr(200, 150, 0.03, 3, empty_rows=True), 4)),  # classes 0, 2, 3
     "lap2d_64": lambda: (laplacian_2d(64),) * 2,                                       # class 1
     "lap3d_8": lambda: (laplacian_3d_27(8),) * 2,                                      # class 2-3 (work up to 729)
     "rand_rect": lambda: (random_csr(120, 200, 0.05, 2, empty_rows=True),
@@ -79,6 +94,20 @@ def test_spgemm_matches_oracle(g4s, oracle, name):
     assert t.total > 0 and abs(t.create + t.spmm + t.export_csr + t.destroy - t.total) < 1e-3
     # reference-style comparison (CSR::operator==, EPSILON 1e-3)
     assert C == g4s.CSR(A[0], B[1], rpt, col, val)
+
+
+def test_tiny_row_classes_are_bit_exact(g4s, oracle):
+    """Classes 1 (k-way merge) and 2 (thread-per-row table) accumulate in the reference's order with separate
+    multiply and add: their values equal HashSpGEMM<false,true>'s bit for bit, not just to 1e-12."""
+    for A, B in ((laplacian_2d(50),) * 2, (random_csr(500, 500, 0.006, 11), random_csr(500, 500, 0.006, 12)),
+                 (shuffled(laplacian_2d(30), 5), shuffled(laplacian_2d(30), 6))):
+        total, work = oracle.intprod(A[2], A[3], B[2])
+        assert work.max() <= 32
+        rpt, col, val = oracle.hash_spgemm(A, B)
+        C = g4s.HashSpGEMM(as_csr(g4s, A), as_csr(g4s, B)).to_host()
+        np.testing.assert_array_equal(C.rowptr, rpt)
+        np.testing.assert_array_equal(C.colids, col)
+        np.testing.assert_array_equal(C.values, val)
 
 
 def test_spgemm_golden_vectors(g4s):
