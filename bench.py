@@ -370,9 +370,8 @@ def bench_spgemm(g4s_b200, torch, args):
     Ah = A.to_host()
     t = g4s_b200.Timings()
     g4s_b200.mkl(Ah, Ah, t)
-    t0 = time.perf_counter()
     g4s_b200.mkl(Ah, Ah, t)
-    e2e_s = time.perf_counter() - t0
+    e2e_s = t.total  # seconds inside g4s_mkl: host CSR in -> host CSR out (upload, multiply, download, frees)
     return {"metric": "spgemm_gflops", "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms": ms,
             "config": {"workload": "SpGEMM C=A*A, 2-D 5-point Laplacian n=%d (BASELINE configs[3])" % SPGEMM_GRID,
                        "rows": rows, "nnzA": nnza, "nnzC": nnzc, "flop": flop},

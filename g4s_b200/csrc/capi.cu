@@ -69,12 +69,17 @@ int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz) {
     h->cols = cols;
     h->nnz = nnz;
     h->owns = true;
-    cudaError_t e = cudaMalloc(&h->rowptr, sizeof(int) * ((size_t)rows + 1) + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&h->colids, sizeof(int) * (size_t)nnz + 64);
-    if (e == cudaSuccess) e = cudaMalloc(&h->values, sizeof(double) * (size_t)nnz + 64);
+    // stream-ordered pool (release threshold = keep): repeated create/destroy cycles, as in the reference's
+    // benchmark loop (mm/src/mkl_spgemm.cpp:67-79), reuse the same device memory instead of paying cudaMalloc/cudaFree
+    h->pooled = true;
+    cudaError_t e = cudaMallocAsync(&h->rowptr, sizeof(int) * ((size_t)rows + 1) + 64, 0);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->colids, sizeof(int) * (size_t)nnz + 64, 0);
+    if (e == cudaSuccess) e = cudaMallocAsync(&h->values, sizeof(double) * (size_t)nnz + 64, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     if (e != cudaSuccess) {
+        cudaGetLastError();
         g4s_csr_destroy(h);
-        return fail(G4S_ERR_ALLOC, std::string("cudaMalloc CSR: ") + cudaGetErrorString(e));
+        return fail(G4S_ERR_ALLOC, std::string("device allocation of CSR: ") + cudaGetErrorString(e));
     }
     *out = h;
     return G4S_OK;
@@ -82,6 +87,96 @@ int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz) {
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+}  // namespace g4s
+
+
+// ---- pageable host memory <-> device through pinned staging ----------------------------------------------------
+// cudaMemcpy on pageable memory runs at a few GB/s (driver-side staging on one thread, plus first-touch page faults
+// on freshly malloc'd destinations).  Large copies go through two pinned 32 MB buffers instead: the PCIe transfer of
+// one piece overlaps the OpenMP-parallel memcpy of the next.  Pinned (or small) host buffers are copied directly.
+namespace {
+constexpr size_t STAGE_BYTES = 32u << 20;
+struct Staging {
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    int device = -1;
+    bool ensure() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (buf[0] && dev == device) return true;
+        device = dev;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaMallocHost(&buf[i], STAGE_BYTES) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        return cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
+    }
+};
+thread_local Staging t_stage;
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t piece = 1u << 20;
+    const long long n = (long long)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; ++i) {
+        const size_t off = (size_t)i * piece;
+        memcpy((char *)dst + off, (const char *)src + off, std::min(piece, bytes - off));
+    }
+}
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+}  // namespace
+
+namespace g4s {
+int copy_h2d(void *dst_dev, const void *src_host, size_t bytes) {
+    if (!bytes) return G4S_OK;
+    if (bytes < (4u << 20) || is_pinned(src_host) || !t_stage.ensure()) {
+        G4S_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+        return G4S_OK;
+    }
+    Staging &st = t_stage;
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += STAGE_BYTES, ++i) {
+        const size_t n = std::min(STAGE_BYTES, bytes - off);
+        const int b = i & 1;
+        if (i >= 2) G4S_CUDA(cudaEventSynchronize(st.ev[b]));  // the transfer that last used this buffer is done
+        parallel_memcpy(st.buf[b], (const char *)src_host + off, n);
+        G4S_CUDA(cudaMemcpyAsync((char *)dst_dev + off, st.buf[b], n, cudaMemcpyHostToDevice, st.stream));
+        G4S_CUDA(cudaEventRecord(st.ev[b], st.stream));
+    }
+    G4S_CUDA(cudaStreamSynchronize(st.stream));
+    return G4S_OK;
+}
+int copy_d2h(void *dst_host, const void *src_dev, size_t bytes) {
+    if (!bytes) return G4S_OK;
+    if (bytes < (4u << 20) || is_pinned(dst_host) || !t_stage.ensure()) {
+        G4S_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+        return G4S_OK;
+    }
+    Staging &st = t_stage;
+    G4S_CUDA(cudaDeviceSynchronize());  // the source was produced on other streams
+    const int pieces = (int)((bytes + STAGE_BYTES - 1) / STAGE_BYTES);
+    auto issue = [&](int i) -> cudaError_t {
+        const size_t off = (size_t)i * STAGE_BYTES, n = std::min(STAGE_BYTES, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(st.buf[i & 1], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, st.stream);
+        return e != cudaSuccess ? e : cudaEventRecord(st.ev[i & 1], st.stream);
+    };
+    G4S_CUDA(issue(0));
+    for (int i = 0; i < pieces; ++i) {
+        if (i + 1 < pieces) G4S_CUDA(issue(i + 1));  // the other buffer was drained in the previous iteration
+        G4S_CUDA(cudaEventSynchronize(st.ev[i & 1]));
+        const size_t off = (size_t)i * STAGE_BYTES, n = std::min(STAGE_BYTES, bytes - off);
+        parallel_memcpy((char *)dst_host + off, st.buf[i & 1], n);
+    }
+    return G4S_OK;
+}
 }  // namespace g4s
 
 // ---- partitioner (BIN::set_rows_offset, mm/inc/BIN.h:100-122) ------------------------------------------
@@ -175,12 +270,12 @@ int g4s_csr_create_host(g4s_csr_t *out, int rows, int cols, const int *rowptr, c
     g4s_csr *h = nullptr;
     rc = alloc_csr(&h, rows, cols, nnz);
     if (rc) return rc;
-    cudaError_t e = cudaMemcpy(h->rowptr, rowptr, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && nnz) e = cudaMemcpy(h->colids, colids, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && nnz) e = cudaMemcpy(h->values, values, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
+    rc = g4s::copy_h2d(h->rowptr, rowptr, sizeof(int) * ((size_t)rows + 1));
+    if (rc == G4S_OK && nnz) rc = g4s::copy_h2d(h->colids, colids, sizeof(int) * (size_t)nnz);
+    if (rc == G4S_OK && nnz) rc = g4s::copy_h2d(h->values, values, sizeof(double) * (size_t)nnz);
+    if (rc != G4S_OK) {
         g4s_csr_destroy(h);
-        return fail(G4S_ERR_CUDA, std::string("H2D copy of CSR: ") + cudaGetErrorString(e));
+        return rc;
     }
     *out = h;
     return G4S_OK;
@@ -249,10 +344,11 @@ int g4s_csr_device_arrays(g4s_csr_t h, const int **rowptr_dev, const int **colid
 
 int g4s_csr_download(g4s_csr_t h, int *rowptr, int *colids, double *values) {
     if (!h) return fail(G4S_ERR_INVALID, "null handle");
-    if (rowptr) G4S_CUDA(cudaMemcpy(rowptr, h->rowptr, sizeof(int) * ((size_t)h->rows + 1), cudaMemcpyDeviceToHost));
-    if (colids && h->nnz) G4S_CUDA(cudaMemcpy(colids, h->colids, sizeof(int) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
-    if (values && h->nnz) G4S_CUDA(cudaMemcpy(values, h->values, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
-    return G4S_OK;
+    int rc = G4S_OK;
+    if (rowptr) rc = g4s::copy_d2h(rowptr, h->rowptr, sizeof(int) * ((size_t)h->rows + 1));
+    if (rc == G4S_OK && colids && h->nnz) rc = g4s::copy_d2h(colids, h->colids, sizeof(int) * (size_t)h->nnz);
+    if (rc == G4S_OK && values && h->nnz) rc = g4s::copy_d2h(values, h->values, sizeof(double) * (size_t)h->nnz);
+    return rc;
 }
 
 // ---- SpMV -----------------------------------------------------------------------------------------------
