@@ -391,14 +391,26 @@ __global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const Spgemm
 // smallest head column and folds every list that carries it, in list order — which is the reference's
 // accumulation order (j ascending over A's row, one entry of B's row per column; hash_mult.h:579-600), so the
 // values are bit-identical to HashSpGEMM<false,true> and the columns come out sorted with no sort at all.
+constexpr int MERGE_STAGE = 16;  // output entries per row staged in shared memory for the coalesced store
 template <bool NUMERIC>
 __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
                                                                int nlist) {
     constexpr int K = MERGE_MAX_A;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nlist;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int row = list ? __ldg(list + idx) : (int)idx;
-        const int as = __ldg(a.arpt + row), na = __ldg(a.arpt + row + 1) - as;
+    constexpr int THREADS = 256;
+    // numeric phase: [MERGE_STAGE][THREADS] columns and values; entry e of lane L sits in column (L + e) & 31 of its
+    // warp's 32 columns, so that both the per-thread writes and the warp's read-back are bank-conflict-free
+    __shared__ int s_col[NUMERIC ? MERGE_STAGE * THREADS : 1];
+    __shared__ double s_val[NUMERIC ? MERGE_STAGE * THREADS : 1];
+    const int t = threadIdx.x, lane = t & 31, tw = t - lane;
+    for (long long base = (long long)blockIdx.x * THREADS; base < nlist; base += (long long)gridDim.x * THREADS) {
+        const long long idx = base + t;
+        const bool active = idx < nlist;
+        const int row = active ? (list ? __ldg(list + idx) : (int)idx) : -1;
+        int as = 0, na = 0;
+        if (active) {
+            as = __ldg(a.arpt + row);
+            na = __ldg(a.arpt + row + 1) - as;
+        }
         int pos[K], end[K], head[K];
         double av[K];
 #pragma unroll
@@ -414,8 +426,18 @@ __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs 
                 if (pos[u] < end[u]) head[u] = __ldg(a.bcol + pos[u]);
             }
         }
+        int out = 0, nrow = 0;
+        bool staged = false;
+        if (NUMERIC) {
+            if (active) {
+                out = __ldg(a.crpt + row);
+                nrow = __ldg(a.crpt + row + 1) - out;
+            }
+            // the warp's 32 rows are consecutive (one contiguous range of C) and short: stage, then store coalesced
+            const int row0 = __shfl_sync(0xffffffffu, row, 0);
+            staged = __all_sync(0xffffffffu, active && row == row0 + lane && nrow <= MERGE_STAGE);
+        }
         int n = 0;
-        const int out = NUMERIC ? __ldg(a.crpt + row) : 0;
         for (;;) {
             int m = head[0];
 #pragma unroll
@@ -436,12 +458,44 @@ __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs 
                 }
             }
             if (NUMERIC) {
-                a.ccol[out + n] = m;
-                a.cval[out + n] = v;
+                if (staged) {
+                    const int col = tw + ((lane + n) & 31);
+                    s_col[n * THREADS + col] = m;
+                    s_val[n * THREADS + col] = v;
+                } else {
+                    a.ccol[out + n] = m;
+                    a.cval[out + n] = v;
+                }
             }
             ++n;
         }
-        if (!NUMERIC) a.row_nnz[row] = n;
+        if (!NUMERIC) {
+            if (active) a.row_nnz[row] = n;
+            continue;
+        }
+        if (staged) {
+            __syncwarp();
+            const int out0 = __shfl_sync(0xffffffffu, out, 0);
+            const int out1 = __shfl_sync(0xffffffffu, out + nrow, 31);
+            for (int ob = out0; ob < out1; ob += 32) {  // warp-uniform trip count: the owner search uses shuffles
+                const int o = min(ob + lane, out1 - 1);
+                int lo = 0, hi = 31;  // owner lane = last lane whose row starts at or before o
+#pragma unroll
+                for (int step = 0; step < 5; ++step) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    const int start_mid = __shfl_sync(0xffffffffu, out, mid);
+                    if (start_mid <= o) lo = mid;
+                    else hi = mid - 1;
+                }
+                const int e = o - __shfl_sync(0xffffffffu, out, lo);
+                if (ob + lane < out1) {
+                    const int col = tw + ((lo + e) & 31);
+                    a.ccol[o] = s_col[e * THREADS + col];
+                    a.cval[o] = s_val[e * THREADS + col];
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
