@@ -578,6 +578,11 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
         G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // carve out exactly what the resident CTAs need: the rest of the 228 KB stays L1 for the x gathers
+        const int pct = std::min(100, (int)((ctas_per_sm * (smem + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+        G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         configured = true;
     }
     long long want = ((long long)(args.nchunks - args.chunk_begin) + WARPS - 1) / WARPS;
@@ -597,11 +602,47 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
 }
 
 constexpr int SPMV_CAP = 1024;
+constexpr int G4S_SPMV_AUTO_SHORT = 12;  // short-row matrices: 256-nnz chunks, 32 warps per SM, 128 KB left as L1
+void spmv_free_plan(g4s_csr *h);
+void spmv_free_host_pipe(g4s_csr *h);
+
+// Kernel shapes (tuning variants).  cap = nonzeros per chunk = size of a warp's staging buffer (12 bytes each);
+// what shared memory the buffers leave becomes L1, which is where scattered x gathers (power-law graphs) live.
+struct SpmvShape {
+    int cap, nbuf, warps, ctas;
+};
+static SpmvShape shape_of(int variant) {
+    switch (variant) {
+        case 1: return {1024, 1, 16, 1};
+        case 2: return {1024, 2, 8, 1};
+        case 3: return {1024, 2, 4, 2};
+        case 4: return {1024, 1, 8, 2};
+        case 5: return {1024, 1, 6, 3};
+        case 7: return {512, 1, 16, 1};
+        case 8: return {512, 1, 24, 1};
+        case 10: return {512, 1, 16, 2};
+        case 11: return {512, 1, 32, 1};
+        case 12: return {256, 1, 32, 1};
+        case 13: return {256, 1, 32, 2};
+        case 14: return {256, 1, 24, 2};
+        default: return {1024, 1, 9, 2};
+    }
+}
+// automatic choice: short-row matrices (32 rows never fill 512 nonzeros) take the small-buffer shape
+static int auto_variant(const g4s_csr *h) {
+    const double avg = h->rows ? (double)h->nnz / h->rows : 0.0;
+    return avg * CHUNK_ROWS <= 512.0 ? G4S_SPMV_AUTO_SHORT : 6;
+}
 
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream) {
     SpmvPlan &p = h->plan;
-    if (p.desc) return G4S_OK;
-    p.cap = SPMV_CAP;
+    const int want_cap = shape_of(p.variant ? p.variant : auto_variant(h)).cap;
+    if (p.desc && p.cap == want_cap) return G4S_OK;
+    if (p.desc) {  // the tuning variant changed the chunk size: cut the rows again
+        spmv_free_host_pipe(h);
+        spmv_free_plan(h);
+    }
+    p.cap = want_cap;
     const int nblocks = (h->rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
     int *counts = nullptr, *stats = nullptr;
     G4S_CUDA(cudaMalloc(&counts, sizeof(int) * ((size_t)nblocks + 1)));
@@ -686,16 +727,25 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
         while ((1 << lg) < p.lanes_per_row && lg < 5) ++lg;
         a.force_lg = lg;
     }
-    // kernel shapes: ring depth x warps per CTA x CTAs per SM.  Measured on B200, 3-D 27-point n=400
-    // (profiles/r01_spmv_sweep.txt): 18 single-buffered warps per SM as 2 CTAs of 9 is the fastest; deeper
-    // per-warp rings with fewer warps lose (resident warps, not per-warp prefetch depth, hide the latency).
-    switch (parts ? 0 : p.variant) {
-        case 1: rc = launch_chunk_kernel<SPMV_CAP, 1, 16>(a, accum, 1, stream); break;
-        case 2: rc = launch_chunk_kernel<SPMV_CAP, 2, 8>(a, accum, 1, stream); break;
-        case 3: rc = launch_chunk_kernel<SPMV_CAP, 2, 4>(a, accum, 2, stream); break;
-        case 4: rc = launch_chunk_kernel<SPMV_CAP, 1, 8>(a, accum, 2, stream); break;
-        case 5: rc = launch_chunk_kernel<SPMV_CAP, 1, 6>(a, accum, 3, stream); break;
-        default: rc = launch_chunk_kernel<SPMV_CAP, 1, 9>(a, accum, 2, stream, parts); break;
+    // kernel shapes: chunk size x ring depth x warps per CTA x CTAs per SM (profiles/r01_spmv_summary.md,
+    // r01_other_kernels_summary.md).  27-nnz stencil rows: 1024-nnz chunks, 18 single-buffered warps per SM as 2 CTAs
+    // of 9 (deeper per-warp rings with fewer warps lose: resident warps hide the latency).  Short or power-law rows
+    // (mean row length <= 16): 256-nnz chunks, 32 warps per SM and the rest of shared memory left to L1.
+    const int variant = parts ? 6 : (p.variant ? p.variant : auto_variant(h));
+    switch (variant) {
+        case 1: rc = launch_chunk_kernel<1024, 1, 16>(a, accum, 1, stream); break;
+        case 2: rc = launch_chunk_kernel<1024, 2, 8>(a, accum, 1, stream); break;
+        case 3: rc = launch_chunk_kernel<1024, 2, 4>(a, accum, 2, stream); break;
+        case 4: rc = launch_chunk_kernel<1024, 1, 8>(a, accum, 2, stream); break;
+        case 5: rc = launch_chunk_kernel<1024, 1, 6>(a, accum, 3, stream); break;
+        case 7: rc = launch_chunk_kernel<512, 1, 16>(a, accum, 1, stream); break;
+        case 8: rc = launch_chunk_kernel<512, 1, 24>(a, accum, 1, stream); break;
+        case 10: rc = launch_chunk_kernel<512, 1, 16>(a, accum, 2, stream); break;
+        case 11: rc = launch_chunk_kernel<512, 1, 32>(a, accum, 1, stream); break;
+        case 12: rc = launch_chunk_kernel<256, 1, 32>(a, accum, 1, stream); break;
+        case 13: rc = launch_chunk_kernel<256, 1, 32>(a, accum, 2, stream); break;
+        case 14: rc = launch_chunk_kernel<256, 1, 24>(a, accum, 2, stream); break;
+        default: rc = launch_chunk_kernel<1024, 1, 9>(a, accum, 2, stream, parts); break;
     }
     if (rc) return rc;
     if (p.n_long > 0 && chunk_end < 0) {  // row-block launches leave the fix-up to the caller
