@@ -17,8 +17,9 @@
 //   class 5  w <= 8192     one 1024-thread CTA per row, 8192 slots
 //   class 6  larger        one CTA per row, power-of-two table in global memory (persistent CTAs own a slab)
 // Classes 1 and 2 keep the reference's sequential accumulation order: their VALUES are bit-identical to it.
-// Hash = (key * 107) & (size-1) with linear probing, empty = -1, exactly the reference's function
-// (hash_mult.h:23, :89-101); insertion uses atomicCAS on the key and atomicAdd(double) on the value, so the
+// Open addressing with linear probing, empty = -1, as the reference (hash_mult.h:89-101), with a multiplicative hash
+// on the high bits instead of (key * 107) & mask (see hash_slot).  Classes 3-6 insert with atomicCAS on the key and
+// atomicAdd(double) on the value, so the
 // accumulation order inside a row differs from the reference's sequential order (values agree to rounding;
 // the sparsity pattern is exact).  Rows are handed out class by class in ascending row order so that
 // neighbouring rows of B stay hot in L1/L2.
@@ -39,16 +40,32 @@ int alloc_csr(g4s_csr **out, int rows, int cols, long long nnz);
 constexpr int NCLASS = 7;
 constexpr int MERGE_MAX_A = 8;    // class 1: rows of A with at most this many entries ...
 constexpr int MERGE_MAX_W = 64;   // ... and at most this many intermediate products, when B's rows are sorted
-constexpr int HASH_MULT = 107;  // mm/inc/hash_mult.h:23
+// Slot of a key in a table of size mask+1 (a power of two): multiplicative (Fibonacci) hashing on the HIGH bits.
+// The reference hashes with (key * 107) & mask (mm/inc/hash_mult.h:23, :89): on grids whose edge is a power of two the
+// stencil columns differ by multiples of 64 / 4096 and that function maps whole planes to the same few slots (A*A on the
+// 64^3 27-point Laplacian ran 6x slower than on 100^3).  The table layout is internal: the output does not depend on it.
+__device__ __forceinline__ int hash_slot(int key, int mask) {
+    return (int)(((unsigned)key * 2654435769u) >> __clz(mask));
+}
 
+// class of a row in the SYMBOLIC phase: the table must hold every distinct column, bounded by w = min(work, cols)
 __host__ __device__ inline int work_class(int work, int cols, int alen, bool b_sorted) {
     const int w = work < cols ? work : cols;
     if (w == 0) return 0;
     if (b_sorted && alen <= MERGE_MAX_A && work <= MERGE_MAX_W) return 1;
     if (w <= 32) return 2;
-    if (w <= 256) return 3;
-    if (w <= 2048) return 4;
-    if (w <= 8192) return 5;
+    if (w <= 1024) return 3;
+    if (w <= 4096) return 4;
+    if (w <= 16384) return 5;
+    return 6;
+}
+// class of a row in the NUMERIC phase: its nnz is known by then, and usually far below w (the 27-point A*A row has
+// 729 products but 125 columns), so the row moves to a smaller table / a smaller thread group
+__host__ __device__ inline int nnz_class(int sym_class, int nnz) {
+    if (sym_class <= 2) return sym_class;
+    if (nnz <= 256) return 3;
+    if (nnz <= 2048) return 4;
+    if (nnz <= 8192) return 5;
     return 6;
 }
 
@@ -95,13 +112,13 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
 
 // rows of each class, ascending inside a block of 256 rows; blocks reserve their ranges with one atomic per class
 __global__ void bin_fill_kernel(const unsigned char *__restrict__ row_class, int M, int *__restrict__ cursor,
-                                int *__restrict__ perm, int *__restrict__ row_nnz) {
+                                int *__restrict__ perm, int *__restrict__ row_nnz) {  // row_nnz null: leave it alone
     __shared__ int wcount[NCLASS][8];
     __shared__ int base[NCLASS];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = i < M ? (int)row_class[i] : -1;
-    if (c == 0) row_nnz[i] = 0;
+    if (c == 0 && row_nnz) row_nnz[i] = 0;
     int my_rank = 0;
 #pragma unroll
     for (int k = 1; k < NCLASS; ++k) {
@@ -123,6 +140,21 @@ __global__ void bin_fill_kernel(const unsigned char *__restrict__ row_class, int
     if (c > 0) perm[base[c] + wcount[c][w] + my_rank] = i;
 }
 
+__global__ void numeric_class_kernel(const unsigned char *__restrict__ sym_class, const int *__restrict__ row_nnz, int M,
+                                     unsigned char *__restrict__ num_class, int *__restrict__ class_count) {
+    __shared__ int hist[NCLASS];
+    if (threadIdx.x < NCLASS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        const int c = nnz_class(sym_class[i], row_nnz[i]);
+        num_class[i] = (unsigned char)c;
+        atomicAdd(&hist[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLASS && hist[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+}
+
 // ---- hash kernels -----------------------------------------------------------------------------------------
 struct SpgemmArgs {
     const int *arpt, *acol;
@@ -134,6 +166,7 @@ struct SpgemmArgs {
     int *ccol;
     double *cval;
     int *row_nnz;
+    const int *row_work;  // intermediate products per row (sizes the symbolic table)
     int sub_lg;  // lanes cooperating on one row of B (log2), chosen from B's mean row length
 };
 
@@ -145,7 +178,7 @@ __device__ __forceinline__ void group_sync() {
 
 // insert key into a power-of-two table; returns true when the key was new
 __device__ __forceinline__ bool hash_insert(int *keys, int mask, int key) {
-    int h = (key * HASH_MULT) & mask;
+    int h = hash_slot(key, mask);
     for (;;) {
         const int cur = keys[h];
         if (cur == key) return false;
@@ -158,7 +191,7 @@ __device__ __forceinline__ bool hash_insert(int *keys, int mask, int key) {
     }
 }
 __device__ __forceinline__ void hash_accumulate(int *keys, double *vals, int mask, int key, double v) {
-    int h = (key * HASH_MULT) & mask;
+    int h = hash_slot(key, mask);
     for (;;) {
         const int cur = keys[h];
         if (cur == key) break;
@@ -192,7 +225,22 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
     for (int base = blockIdx.x * RPC; base < nlist; base += gridDim.x * RPC) {
         const int idx = base + g;
         const int row = idx < nlist ? (list ? __ldg(list + idx) : idx) : -1;
-        for (int s = lane; s < TABLE; s += GROUP) {
+        // The table is a power-of-two prefix of the class's TABLE slots, sized for this row at load factor <= 1/2:
+        // by the row's intermediate products in the symbolic phase, by its now-known nnz in the numeric phase.
+        int out = 0, nrow = 0, want = 0;
+        if (row >= 0) {
+            if (NUMERIC) {
+                out = __ldg(a.crpt + row);
+                nrow = __ldg(a.crpt + row + 1) - out;
+                want = 2 * nrow;
+            } else {
+                want = 2 * min(__ldg(a.row_work + row), a.N);
+            }
+        }
+        int tsize = 32;
+        while (tsize < want && tsize < TABLE) tsize <<= 1;
+        const int mask = tsize - 1;
+        for (int s = lane; s < tsize; s += GROUP) {
             mykeys[s] = -1;
             if (NUMERIC) myvals[s] = 0.0;
         }
@@ -207,9 +255,9 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
                 if (NUMERIC) {
                     const double av = __ldg(a.aval + j);
                     for (int p = bs + sl; p < be; p += SUB)
-                        hash_accumulate(mykeys, myvals, TABLE - 1, __ldg(a.bcol + p), av * __ldg(a.bval + p));
+                        hash_accumulate(mykeys, myvals, mask, __ldg(a.bcol + p), av * __ldg(a.bval + p));
                 } else {
-                    for (int p = bs + sl; p < be; p += SUB) fresh += hash_insert(mykeys, TABLE - 1, __ldg(a.bcol + p));
+                    for (int p = bs + sl; p < be; p += SUB) fresh += hash_insert(mykeys, mask, __ldg(a.bcol + p));
                 }
             }
         }
@@ -226,10 +274,10 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
             group_sync<GROUP>();
         } else {
             group_sync<GROUP>();
-            // compact the occupied slots, then rank-sort by column straight into C's row
+            // compact the occupied slots
             int *myck = ckeys + g * WMAX;
             double *mycv = cvals + g * WMAX;
-            for (int s = lane; s < TABLE; s += GROUP) {
+            for (int s = lane; s < tsize; s += GROUP) {
                 const int key = mykeys[s];
                 if (key != -1) {
                     const int pos = atomicAdd(&cnt[g], 1);
@@ -238,15 +286,43 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
                 }
             }
             group_sync<GROUP>();
-            if (row >= 0) {
-                const int n = cnt[g];
-                const int out = __ldg(a.crpt + row);
+            const int n = nrow;
+            if (n <= 128) {
+                // short rows: rank sort straight into C's row (n^2 / GROUP comparisons, no barriers)
                 for (int e = lane; e < n; e += GROUP) {
                     const int key = myck[e];
                     int rank = 0;
                     for (int f = 0; f < n; ++f) rank += myck[f] < key;
                     a.ccol[out + rank] = key;
                     a.cval[out + rank] = mycv[e];
+                }
+            } else {
+                // longer rows: bitonic sort of the compacted (column, value) pairs in shared memory
+                int n2 = 256;
+                while (n2 < n) n2 <<= 1;
+                for (int e = n + lane; e < n2; e += GROUP) myck[e] = 0x7fffffff;
+                group_sync<GROUP>();
+                for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                        for (int i = lane; i < n2; i += GROUP) {
+                            const int partner = i ^ j2;
+                            if (partner > i) {
+                                const int ki = myck[i], kp = myck[partner];
+                                if ((ki > kp) == ((i & k2) == 0)) {
+                                    myck[i] = kp;
+                                    myck[partner] = ki;
+                                    const double vi = mycv[i];
+                                    mycv[i] = mycv[partner];
+                                    mycv[partner] = vi;
+                                }
+                            }
+                        }
+                        group_sync<GROUP>();
+                    }
+                }
+                for (int e = lane; e < n; e += GROUP) {
+                    a.ccol[out + e] = myck[e];
+                    a.cval[out + e] = mycv[e];
                 }
             }
             group_sync<GROUP>();
@@ -300,7 +376,7 @@ __global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const Spgemm
                             const int key = kk[u];
                             double prod = 0.0;
                             if (NUMERIC) prod = __dmul_rn(av, vv[u]);
-                            int h = (key * HASH_MULT) & (TABLE - 1);
+                            int h = hash_slot(key, TABLE - 1);
                             for (;;) {
                                 const int cur = keys[h * THREADS + t];
                                 if (cur == key) {
@@ -525,7 +601,7 @@ __global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a,
               sl = threadIdx.x & (SUB - 1);
     for (int idx = blockIdx.x; idx < nlist; idx += gridDim.x) {
         const int row = list ? list[idx] : idx;
-        const int w = min(row_work[row], a.N);
+        const int w = NUMERIC ? a.crpt[row + 1] - a.crpt[row] : min(row_work[row], a.N);
         long long tsize = 16384;
         while (tsize < 2LL * w) tsize <<= 1;
         if (tsize > slab_slots) tsize = slab_slots;
@@ -598,24 +674,21 @@ __global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a,
 
 static thread_local double t_phase_ms[4] = {0, 0, 0, 0};
 
-template <int GROUP, int TABLE, int WMAX, int THREADS>
-static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
+template <int GROUP, int TABLE, int WMAX, int THREADS, bool NUMERIC>
+static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, cudaStream_t stream) {
     if (nlist == 0) return G4S_OK;
     constexpr int RPC = THREADS / GROUP;
-    const size_t smem_sym = sizeof(int) * (RPC * TABLE + RPC) + 16;
-    const size_t smem_num = sizeof(double) * (RPC * TABLE + RPC * WMAX) + sizeof(int) * (RPC * TABLE + RPC * WMAX + RPC) + 16;
-    auto ks = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, false>;
-    auto kn = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, true>;
+    const size_t smem = NUMERIC ? sizeof(double) * (RPC * TABLE + RPC * WMAX) + sizeof(int) * (RPC * TABLE + RPC * WMAX + RPC) + 16
+                                : sizeof(int) * (RPC * TABLE + RPC) + 16;
+    auto k = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, NUMERIC>;
     static bool configured = false;
     if (!configured) {
-        G4S_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sym));
-        G4S_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_num));
+        G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const long long want = ((long long)nlist + RPC - 1) / RPC;
     const int grid = (int)std::min<long long>(want, (long long)sm_count() * 16);
-    if (numeric) kn<<<grid, THREADS, smem_num, stream>>>(a, list, nlist);
-    else ks<<<grid, THREADS, smem_sym, stream>>>(a, list, nlist);
+    k<<<grid, THREADS, smem, stream>>>(a, list, nlist);
     G4S_CHECK_LAUNCH("spgemm_smem_kernel");
     return G4S_OK;
 }
@@ -662,9 +735,15 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
         G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
     }
     if ((rc = launch_thread_row<32, 128>(a, list(2), b.count[2], numeric, stream))) return rc;
-    if ((rc = launch_smem<32, 512, 256, 256>(a, list(3), b.count[3], numeric, stream))) return rc;
-    if ((rc = launch_smem<256, 4096, 2048, 256>(a, list(4), b.count[4], numeric, stream))) return rc;
-    if ((rc = launch_smem<1024, 8192, 8192, 1024>(a, list(5), b.count[5], numeric, stream))) return rc;
+    if (numeric) {  // tables sized by nnz (load factor <= 1/2 up to the class bound), values + compaction buffers
+        if ((rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream))) return rc;
+        if ((rc = launch_smem<256, 4096, 2048, 256, true>(a, list(4), b.count[4], stream))) return rc;
+        if ((rc = launch_smem<1024, 8192, 8192, 1024, true>(a, list(5), b.count[5], stream))) return rc;
+    } else {        // keys only, sized by min(work, cols)
+        if ((rc = launch_smem<32, 1024, 1, 256, false>(a, list(3), b.count[3], stream))) return rc;
+        if ((rc = launch_smem<256, 4096, 1, 256, false>(a, list(4), b.count[4], stream))) return rc;
+        if ((rc = launch_smem<1024, 16384, 1, 1024, false>(a, list(5), b.count[5], stream))) return rc;
+    }
     if (b.count[6]) {
         if (numeric)
             spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
@@ -683,7 +762,8 @@ struct Workspace {
     int device = -1;
     size_t rows_cap = 0;
     int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
-    unsigned char *row_class = nullptr;
+    unsigned char *row_class = nullptr, *num_class = nullptr;
+    int *perm2 = nullptr;
     unsigned long long *dtotal = nullptr;
     int *hcount = nullptr;  // pinned
     unsigned long long *htotal = nullptr;
@@ -696,9 +776,9 @@ struct Workspace {
             device = dev;
         }
         if (!dcount) {
-            G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (2 * NCLASS + 1)));
+            G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (4 * NCLASS + 2)));
             G4S_CUDA(cudaMalloc(&dtotal, sizeof(unsigned long long)));
-            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (2 * NCLASS + 1)));
+            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 2)));
             G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
             for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
         }
@@ -707,11 +787,15 @@ struct Workspace {
             if (perm) cudaFree(perm);
             if (row_nnz) cudaFree(row_nnz);
             if (row_class) cudaFree(row_class);
+            if (num_class) cudaFree(num_class);
+            if (perm2) cudaFree(perm2);
             rows_cap = (size_t)M + 1;
             G4S_CUDA(cudaMalloc(&row_work, sizeof(int) * rows_cap));
             G4S_CUDA(cudaMalloc(&perm, sizeof(int) * rows_cap));
             G4S_CUDA(cudaMalloc(&row_nnz, sizeof(int) * rows_cap));
             G4S_CUDA(cudaMalloc(&row_class, rows_cap));
+            G4S_CUDA(cudaMalloc(&num_class, rows_cap));
+            G4S_CUDA(cudaMalloc(&perm2, sizeof(int) * rows_cap));
         }
         return G4S_OK;
     }
@@ -732,7 +816,7 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     b.perm = ws.perm;
     int *row_nnz = ws.row_nnz;
     int *dcount = ws.dcount;
-    G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int) * (2 * NCLASS + 1), stream));
+    G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int) * (4 * NCLASS + 2), stream));
     G4S_CUDA(cudaMemsetAsync(ws.dtotal, 0, sizeof(unsigned long long), stream));
     const int threads = 256;
     const int blocks = (M + threads - 1) / threads;
@@ -783,21 +867,23 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
         const double avg = B->rows ? (double)B->nnz / B->rows : 1.0;
         while ((1 << sub_lg) < avg && sub_lg < 5) ++sub_lg;
     }
-    // global-memory slabs for class 5
+    // global-memory slabs for class 6 (either phase): persistent CTAs, one slab each
     int *slab_keys = nullptr;
     double *slab_vals = nullptr;
     long long slab_slots = 0;
     int slab_ctas = 0;
-    if (b.count[6]) {
+    auto ensure_slabs = [&](int rows_in_class) -> int {
+        if (!rows_in_class || slab_keys) return G4S_OK;
         const long long w = std::min<long long>(b.max_work, N);
         slab_slots = 16384;
         while (slab_slots < 2 * w) slab_slots <<= 1;
         const long long budget = 2LL << 30;  // bytes of scratch
         slab_ctas = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 2, budget / (slab_slots * 12)));
-        slab_ctas = std::min(slab_ctas, b.count[6]);
         G4S_CUDA(cudaMallocAsync(&slab_keys, sizeof(int) * (size_t)slab_slots * slab_ctas, stream));
         G4S_CUDA(cudaMallocAsync(&slab_vals, sizeof(double) * (size_t)slab_slots * slab_ctas, stream));
-    }
+        return G4S_OK;
+    };
+    if ((rc = ensure_slabs(b.count[6]))) return rc;
 
     SpgemmArgs a;
     a.arpt = A->rowptr;
@@ -812,6 +898,7 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     a.ccol = nullptr;
     a.cval = nullptr;
     a.row_nnz = row_nnz;
+    a.row_work = b.row_work;
     a.sub_lg = sub_lg;
 
     // ---- symbolic ---------------------------------------------------------------------------------------------
@@ -827,6 +914,15 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     C->owns = true;
     C->pooled = true;
     G4S_CUDA(cudaMallocAsync(&C->rowptr, sizeof(int) * ((size_t)M + 1) + 64, stream));
+    // numeric classes (by nnz) are counted while the scan runs; both results come back with the scan's one sync
+    int *dcount2 = dcount + 2 * NCLASS + 1;
+    // rows of classes 1 and 2 never move; if one of them holds every row there is nothing to re-bin
+    const bool rebin = M > 0 && !(b.identity && (b.count[1] == M || b.count[2] == M));
+    if (rebin) {
+        numeric_class_kernel<<<blocks, threads, 0, stream>>>(ws.row_class, row_nnz, M, ws.num_class, dcount2);
+        G4S_CHECK_LAUNCH("numeric_class_kernel");
+        G4S_CUDA(cudaMemcpyAsync(ws.hcount + 2 * NCLASS + 1, dcount2, sizeof(int) * NCLASS, cudaMemcpyDeviceToHost, stream));
+    }
     long long cnnz = 0;
     rc = exclusive_scan_i32(row_nnz, C->rowptr, M, 1, &cnnz, stream);
     if (rc == G4S_OK && cnnz > 2147483647LL) rc = fail(G4S_ERR_INVALID, "g4s_spgemm: nnz(C) exceeds int32 row pointers");
@@ -843,7 +939,31 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     a.crpt = C->rowptr;
     a.ccol = C->colids;
     a.cval = C->values;
-    rc = run_phase(a, b, true, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
+    Bins bn = b;
+    if (rebin) {
+        const int *h2 = ws.hcount + 2 * NCLASS + 1;
+        int cur2[NCLASS], off = 0;
+        bn.identity = false;
+        for (int c = 0; c < NCLASS; ++c) {
+            bn.count[c] = h2[c];
+            cur2[c] = off;
+            bn.offset[c] = off;
+            if (c) off += bn.count[c];
+            if (c && bn.count[c] == M) bn.identity = true;
+        }
+        bn.offset[NCLASS] = off;
+        bn.perm = ws.perm2;
+        if (!bn.identity) {
+            G4S_CUDA(cudaMemcpyAsync(dcount2 + NCLASS, cur2, sizeof(cur2), cudaMemcpyHostToDevice, stream));
+            bin_fill_kernel<<<blocks, threads, 0, stream>>>(ws.num_class, M, dcount2 + NCLASS, bn.perm, nullptr);
+            G4S_CHECK_LAUNCH("bin_fill_kernel");
+        }
+        if ((rc = ensure_slabs(bn.count[6]))) {
+            g4s_csr_destroy(C);
+            return rc;
+        }
+    }
+    rc = run_phase(a, bn, true, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
     if (rc) {
         g4s_csr_destroy(C);
         return rc;
