@@ -101,6 +101,58 @@ __global__ void __launch_bounds__(256) bsr3_spmm64_fma_kernel(int mb, const int 
     }
 }
 
+// Multi-GPU form of the DFMA kernel (one NVSwitch box, <= 8 GPUs): the dense operand B is row-partitioned like the block
+// rows, every rank keeps its slice in CUDA-IPC-shared memory, and the kernel reads the rows of B that other GPUs own
+// straight over NVLink — no halo exchange, no replicated B.  base[q] points at block row cut[q] of B.
+struct BParts {
+    const double *base[8];
+    int cut[9];
+    int world;
+};
+__device__ __forceinline__ const double *b_part_row(const BParts &bp, int J) {
+    const double *b = bp.base[0];
+    int cut = bp.cut[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        const bool ge = i < bp.world && J >= bp.cut[i];
+        b = ge ? bp.base[i] : b;
+        cut = ge ? bp.cut[i] : cut;
+    }
+    return b + (size_t)(J - cut) * 3 * 64;
+}
+__global__ void __launch_bounds__(256) bsr3_spmm64_fma_parts_kernel(int mb, const int *__restrict__ browptr,
+                                                                    const int *__restrict__ bcolids,
+                                                                    const double *__restrict__ bvalues,
+                                                                    const BParts bp, double *__restrict__ C) {
+    const int lane = threadIdx.x & 31;
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+        const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        double2 c0 = make_double2(0, 0), c1 = c0, c2 = c0;
+        for (int p = p0; p < p1; ++p) {
+            const int J = __ldg(bcolids + p);
+            const double *blk = bvalues + (size_t)p * 9;
+            const double2 *b = reinterpret_cast<const double2 *>(b_part_row(bp, J)) + lane;
+            const double2 b0 = __ldg(b), b1 = __ldg(b + 32), b2 = __ldg(b + 64);
+            const double a00 = __ldg(blk), a01 = __ldg(blk + 1), a02 = __ldg(blk + 2), a10 = __ldg(blk + 3),
+                         a11 = __ldg(blk + 4), a12 = __ldg(blk + 5), a20 = __ldg(blk + 6), a21 = __ldg(blk + 7),
+                         a22 = __ldg(blk + 8);
+            c0.x = fma(a00, b0.x, c0.x); c0.y = fma(a00, b0.y, c0.y);
+            c0.x = fma(a01, b1.x, c0.x); c0.y = fma(a01, b1.y, c0.y);
+            c0.x = fma(a02, b2.x, c0.x); c0.y = fma(a02, b2.y, c0.y);
+            c1.x = fma(a10, b0.x, c1.x); c1.y = fma(a10, b0.y, c1.y);
+            c1.x = fma(a11, b1.x, c1.x); c1.y = fma(a11, b1.y, c1.y);
+            c1.x = fma(a12, b2.x, c1.x); c1.y = fma(a12, b2.y, c1.y);
+            c2.x = fma(a20, b0.x, c2.x); c2.y = fma(a20, b0.y, c2.y);
+            c2.x = fma(a21, b1.x, c2.x); c2.y = fma(a21, b1.y, c2.y);
+            c2.x = fma(a22, b2.x, c2.x); c2.y = fma(a22, b2.y, c2.y);
+        }
+        double2 *c = reinterpret_cast<double2 *>(C + (size_t)I * 3 * 64) + lane;
+        c[0] = c0;
+        c[32] = c1;
+        c[64] = c2;
+    }
+}
+
 template <int BS>
 __global__ void __launch_bounds__(256) bsr_spmm_generic_kernel(int mb, const int *__restrict__ browptr,
                                                                const int *__restrict__ bcolids,
@@ -144,6 +196,25 @@ extern "C" {
 int g4s_bsr_spmm_set_variant(int variant) {
     if (variant < 0 || variant > 3) return fail(G4S_ERR_INVALID, "variant must be 0 (auto), 1 (fma), 2 (dmma) or 3 (generic)");
     g_bsr_variant = variant;
+    return G4S_OK;
+}
+
+int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, const int *bcolids_dev,
+                                       const double *bvalues_dev, int world, const double *const *B_parts,
+                                       const int *cuts, double *C_dev, void *stream) {
+    if (mb_local < 0 || !browptr_dev || !B_parts || !cuts || !C_dev || world < 1 || world > 8)
+        return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_partitioned_device: bad arguments (1 <= world <= 8)");
+    if (mb_local == 0) return G4S_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    BParts bp;
+    for (int q = 0; q < 8; ++q) bp.base[q] = q < world ? B_parts[q] : nullptr;
+    for (int q = 0; q <= 8; ++q) bp.cut[q] = cuts[q < world ? q : world];
+    bp.world = world;
+    const int grid = (int)std::min<long long>(((long long)mb_local * 32 + 255) / 256, (long long)sm_count() * 16);
+    bsr3_spmm64_fma_parts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev, bvalues_dev, bp,
+                                                                       C_dev);
+    G4S_CHECK_LAUNCH("bsr3_spmm64_fma_parts_kernel");
     return G4S_OK;
 }
 

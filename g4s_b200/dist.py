@@ -349,3 +349,66 @@ class DistSpGEMM:
         offset = int(every[:self.rank].sum().item())
         self.global_nnz = int(every.sum().item())
         return C_local, offset
+
+
+# ------------------------------------------------------------------------------------------------ BSR SpMM
+class DistBsrSpMM:
+    """C = A_bsr B (3x3 blocks, 64 dense columns) with block rows cut over the ranks of one NVSwitch box.
+
+    Every rank holds its block rows (GLOBAL block-column ids) and the matching rows of B in a CUDA-IPC-shared
+    buffer (`self.B_local`, shape [local_block_rows * 3, 64]); the kernel reads the rows of B owned by other GPUs
+    straight over NVLink (g4s_bsr3_spmm64_partitioned_device).  No halo exchange and no replicated B: at the
+    256^3-node size of BASELINE config 5, B is 25.8 GB and a replica per GPU would cost more than the matrix."""
+
+    def __init__(self, browptr, bcolids, bvalues, cuts, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("peer-memory BSR SpMM supports up to 8 GPUs (one NVSwitch box)")
+        self.cuts = [int(c) for c in cuts]
+        self.mb = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        self.browptr, self.bcolids, self.bvalues = browptr, bcolids, bvalues  # device tensors (int32, int32, float64)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        L = lib()
+        ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+        nbytes = 8 * 3 * 64 * max(self.mb, 1)
+        check(L.g4s_peer_alloc(C.c_size_t(nbytes), C.byref(ptr), h))
+        self._own = ptr.value
+        every = [None] * self.world
+        dist.all_gather_object(every, bytes(h), group=self.group)
+        self._opened = []
+        self._parts = (C.c_void_p * self.world)()
+        for q in range(self.world):
+            if q == self.rank:
+                self._parts[q] = self._own
+            else:
+                p = C.c_void_p()
+                check(L.g4s_peer_open((C.c_ubyte * 64).from_buffer_copy(every[q]), C.byref(p)))
+                self._parts[q] = p.value
+                self._opened.append(p.value)
+        self.B_local = torch.as_tensor(_DevArray(self._own, max(self.mb, 1) * 3 * 64, "<f8"), device=dev)[:self.mb * 3 * 64] \
+            .view(self.mb * 3, 64)
+        self._cuts_c = (C.c_int * (self.world + 1))(*self.cuts)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier(group=self.group)
+
+    def apply(self, C_local, sync=True):
+        """C_local[local_block_rows * 3, 64] = (A B)[owned rows].  sync=True orders the product after every rank's
+        writes to its slice of B with a 4-byte all-reduce on the current stream."""
+        if sync:
+            dist.all_reduce(self._flag, group=self.group)
+        check(lib().g4s_bsr3_spmm64_partitioned_device(
+            C.c_int(self.mb), C.c_void_p(self.browptr.data_ptr()), C.c_void_p(self.bcolids.data_ptr()),
+            C.c_void_p(self.bvalues.data_ptr()), C.c_int(self.world), self._parts, self._cuts_c,
+            C.c_void_p(C_local.data_ptr()), _stream_ptr(torch.cuda.current_stream())))
+        return C_local
+
+    def close(self):
+        if self._own:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for p in self._opened:
+                lib().g4s_peer_close(C.c_void_p(p))
+            dist.barrier(group=self.group)
+            lib().g4s_peer_free(C.c_void_p(self._own))
+            self._own, self._opened = None, []
