@@ -287,6 +287,9 @@ def run_ours(args, rank, world):
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = total_bytes / (e2e_s / args.steps) / 1e9
 
+    spgemm_multi = None
+    if dist is not None and not args.no_spgemm:
+        spgemm_multi = bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -323,6 +326,8 @@ def run_ours(args, rank, world):
         "roofline": {"bound": "hbm", "kernel": "spmv_chunk_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic},
     }
+    if spgemm_multi is not None:
+        line["spgemm"] = spgemm_multi
     if world == 1 and not args.no_cpu:
         from oracle.binding import Oracle, Ref
 
@@ -340,6 +345,49 @@ def run_ours(args, rank, world):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world):
+    """configs[3] on N GPUs: A's rows cut over the ranks (rows of the 2-D Laplacian carry near-equal work, so the nnz
+    cut is the work cut), B generated on rank 0 and replicated with NCCL broadcast, every rank multiplies its block."""
+    import ctypes as C
+
+    from g4s_b200.dist import DistSpGEMM, partition_by_prefix
+
+    L = g4s_b200.lib()
+    n = SPGEMM_GRID
+    cuts = partition_by_prefix(lambda r: int(L.g4s_laplacian2d_nnz(C.c_int(n), C.c_longlong(0), C.c_longlong(r))),
+                               n * n, world)
+    A_local = g4s_b200.CSR.laplacian2d(n, cuts[rank], cuts[rank + 1])
+    B = g4s_b200.CSR.laplacian2d(n) if rank == 0 else None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mm = DistSpGEMM(A_local, B, cuts)
+    torch.cuda.synchronize()
+    bcast_s = time.perf_counter() - t0
+    flop_local = 2.0 * g4s_b200.compute_flop(A_local, mm.B)
+    for _ in range(3):
+        mm.multiply()[0].make_empty()
+    dist.barrier()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        Cl, _ = mm.multiply()
+        Cl.make_empty()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps, flop_local], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t)
+    ms, flop = float(tmax[0].item()), float(t[1].item())
+    return {"metric": "spgemm_gflops", "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms": ms, "n_gpus": world,
+            "config": {"workload": "SpGEMM C=A*A, 2-D 5-point Laplacian n=%d (BASELINE configs[3]); A row-partitioned, "
+                                   "B replicated by NCCL broadcast (%.1f ms, once), C left distributed" % (n, bcast_s * 1e3),
+                       "nnzC": mm.global_nnz, "flop": flop}}
 
 
 def bench_spgemm(g4s_b200, torch, args):
