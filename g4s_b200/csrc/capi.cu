@@ -56,7 +56,8 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
 int spmv_host_pipelined(g4s_csr *h, const double *x, double *y);
 void spmv_free_host_pipe(g4s_csr *h);
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
-                         const unsigned long long *flags, unsigned long long epoch, cudaStream_t stream);
+                         const unsigned long long *flags, unsigned long long epoch,
+                         unsigned long long *const *signal_arrays, cudaStream_t stream);
 int peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, cudaStream_t stream);
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream);
 void spmv_free_plan(g4s_csr *h);
@@ -370,11 +371,12 @@ int g4s_spmv_device_ex(g4s_csr_t A, const double *x_dev, double *y_dev, const in
 
 int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
                                 double *y_dev, const unsigned long long *ready_flags_dev, unsigned long long epoch,
-                                void *stream) {
+                                unsigned long long *const *signal_arrays, void *stream) {
     if (!A || !x_parts || !cuts || (!y_dev && A->rows)) return fail(G4S_ERR_INVALID, "g4s_spmv_partitioned_device: null argument");
     int rc = ensure_device();
     if (rc) return rc;
-    return spmv_run_partitioned(A, world, self, x_parts, cuts, y_dev, ready_flags_dev, epoch, (cudaStream_t)stream);
+    return spmv_run_partitioned(A, world, self, x_parts, cuts, y_dev, ready_flags_dev, epoch, signal_arrays,
+                                (cudaStream_t)stream);
 }
 
 int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, void *stream) {

@@ -293,6 +293,8 @@ struct XParts {
     // readiness flags written by the owners (flags[q] >= epoch: rank q's slice for this product is in place)
     const unsigned long long *flags;
     unsigned long long epoch;
+    unsigned long long *signal[MAX_PARTS];  // every rank's flag array (peer-mapped), or null: the caller signals
+    int self;
 };
 __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
     if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
@@ -436,20 +438,34 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
 
     const int wglobal = a.chunk_begin + blockIdx.x * WARPS + warp;
     const int stride = gridDim.x * WARPS;
+    // this warp's chunks are wglobal, wglobal + stride, ...: nit of them, in ascending order, so that at any moment
+    // the whole grid works on one narrow band of rows and x is reused out of L1/L2.  (Starting the CTAs at 8 different
+    // phases of the sweep, to de-synchronise the NVLink-bound chunks at the ends of a rank's range, was measured:
+    // 8 bands cost more in x re-reads — 0.42 -> 0.52 ms on 8 M rows — than the de-synchronisation gains.)
+    const int nit = wglobal < a.nchunks ? (int)(((long long)a.nchunks - wglobal + stride - 1) / stride) : 0;
+    auto chunk_at = [&](int i) -> long long { return (long long)wglobal + (long long)i * stride; };
+    if (PART && xp.flags && xp.signal[0] && blockIdx.x == 0 && warp == 0 && lane < xp.world) {
+        // publish this rank's slice for this product (it was written before the launch): a release store of the epoch
+        // into every rank's flag array, slot self — the separate signal launch is folded into the product
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xp.signal[lane] + xp.self), "l"(xp.epoch) : "memory");
+    }
     if (lane == 0) {
         policy = policy_evict_first();
         for (int b = 0; b < NBUF; ++b) mbar_init(&bar[b], 1);
         fence_mbar_init();
         for (int b = 0; b < NBUF; ++b) {
-            const long long c = (long long)wglobal + (long long)b * stride;
-            if (c < a.nchunks) issue(b, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
+            if (b < nit) {
+                const long long c = chunk_at(b);
+                issue(b, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
+            }
         }
     }
     __syncwarp();
 
     bool peers_ready = !PART || xp.flags == nullptr;
-    int it = 0;
-    for (long long c = wglobal; c < a.nchunks; c += stride, ++it) {
+    for (int it = 0; it < nit; ++it) {
+        const long long c = chunk_at(it);
         const int b = it % NBUF;
         const uint32_t parity = (it / NBUF) & 1;
         const int2 d0 = __ldg(a.desc + c), d1 = __ldg(a.desc + c + 1);
@@ -463,9 +479,10 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
             rp0 = __ldg(a.rowptr + d0.x + (lane >> lg));
             rp1 = __ldg(a.rowptr + d0.x + (lane >> lg) + 1);
         }
-        const long long next = c + (long long)NBUF * stride;
+        const bool has_next = it + NBUF < nit;
         int2 n0 = make_int2(0, 0), n1 = n0;
-        if (lane == 0 && next < a.nchunks) {
+        if (lane == 0 && has_next) {
+            const long long next = chunk_at(it + NBUF);
             n0 = __ldg(a.desc + next);
             n1 = __ldg(a.desc + next + 1);
         }
@@ -492,7 +509,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         }
 #undef G4S_CHUNK_CASE
         __syncwarp();  // every lane is done reading slot b
-        if (lane == 0 && next < a.nchunks) issue(b, n0.y, n1.y);
+        if (lane == 0 && has_next) issue(b, n0.y, n1.y);
     }
     // one warp per GPU always observes every rank's flag before the kernel ends, even when no chunk was remote:
     // a rank can then never run two products ahead of a peer that still reads its double-buffered slice
@@ -594,6 +611,8 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     none.self_base = nullptr;
     none.flags = nullptr;
     none.epoch = 0;
+    none.self = 0;
+    for (int q = 0; q < MAX_PARTS; ++q) none.signal[q] = nullptr;
     if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
     else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
     else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
@@ -756,7 +775,8 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
 }
 
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
-                         const unsigned long long *flags, unsigned long long epoch, cudaStream_t stream) {
+                         const unsigned long long *flags, unsigned long long epoch,
+                         unsigned long long *const *signal_arrays, cudaStream_t stream) {
     if (world < 1 || world > MAX_PARTS || self < 0 || self >= world)
         return fail(G4S_ERR_INVALID, "partitioned SpMV supports 1..8 parts (one NVSwitch box)");
     XParts xp;
@@ -768,6 +788,8 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     xp.self_base = x_parts[self];
     xp.flags = flags;
     xp.epoch = epoch;
+    xp.self = self;
+    for (int q = 0; q < MAX_PARTS; ++q) xp.signal[q] = (signal_arrays && flags && q < world) ? signal_arrays[q] : nullptr;
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     SpmvPlan &p = h->plan;

@@ -210,7 +210,7 @@ class DistSpMV:
         self._cuts_c = (C.c_int * (self.world + 1))(*self.cuts)
         self._flag_arrays = self._parts.pop()
         self._k = 0
-        self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 2
+        self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 1
         dist.barrier(group=self.group)
 
     def next_x(self):
@@ -267,10 +267,11 @@ class DistSpMV:
                 xb.copy_(x_local)
             st = _stream_ptr(torch.cuda.current_stream())
             epoch = C.c_ulonglong(self._k)  # products are numbered from 1; flags start at 0
-            check(lib().g4s_peer_signal(self._flag_arrays, C.c_int(self.world), C.c_int(self.rank), epoch, st))
+            # one launch: the kernel publishes this rank's epoch (release store into every peer's flag array) when it
+            # starts and waits for the owners' flags only in the chunks that read their slices
             check(lib().g4s_spmv_partitioned_device(self.A.handle, C.c_int(self.world), C.c_int(self.rank),
                                                     self._parts[b], self._cuts_c, C.c_void_p(y_local.data_ptr()),
-                                                    C.c_void_p(self._own[2]), epoch, st))
+                                                    C.c_void_p(self._own[2]), epoch, self._flag_arrays, st))
             return y_local
         if ops.device_type != "cuda":
             return self._apply_sync(x_local, y_local)

@@ -173,10 +173,12 @@ int g4s_csr_split_columns(g4s_csr_t A, int c0, int c1, g4s_csr_t *diag, g4s_csr_
  * kernel.  Ordering against the owners' writes is either the caller's (ready_flags_dev == NULL: run a barrier first)
  * or in-kernel: ready_flags_dev points at this rank's array of `world` 64-bit flags in peer-shared memory, into
  * which rank q stores `epoch` with g4s_peer_signal once its slice for this product is written; only the chunks
- * that touch another GPU's slice wait (acquire) for flags >= epoch, the rest of the matrix streams meanwhile. */
+ * that touch another GPU's slice wait (acquire) for flags >= epoch, the rest of the matrix streams meanwhile.
+ * signal_arrays (host array of `world` peer-mapped flag arrays, as for g4s_peer_signal) non-NULL folds the signal into
+ * the product: the kernel publishes `epoch` for this rank's slice when it starts, so a step is ONE launch. */
 int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
                                 double *y_dev, const unsigned long long *ready_flags_dev, unsigned long long epoch,
-                                void *stream);
+                                unsigned long long *const *signal_arrays, void *stream);
 /* flag_arrays[q] = rank q's flag array (own or IPC-mapped).  Stream-ordered after the writes of the x slice:
  * stores `epoch` into slot `self` of every rank's array (release, system scope). */
 int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch,

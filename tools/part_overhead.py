@@ -35,6 +35,6 @@ nbytes, _ = A.spmv_cost()
 t0 = timeit(lambda: A.spmv_device(x.data_ptr(), y.data_ptr()))
 t1 = timeit(lambda: check(L.g4s_spmv_partitioned_device(A.handle, C.c_int(1), C.c_int(0), parts, cuts,
                                                         C.c_void_p(y.data_ptr()), C.c_void_p(0), C.c_ulonglong(0),
-                                                        C.c_void_p(0))))
+                                                        None, C.c_void_p(0))))
 print("n=%d plain %.4f ms (%.0f GB/s)   partitioned(world=1) %.4f ms (%.0f GB/s)" %
       (n, t0, nbytes / t0 / 1e6, t1, nbytes / t1 / 1e6))
