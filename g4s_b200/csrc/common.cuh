@@ -49,6 +49,9 @@ struct SpmvPlan {
     int max_row_len = 0;
     int lanes_per_row = 0;              // tuning override, 0 = inspector's choice
     int variant = 0;                    // tuning override, 0 = default kernel shape
+    int built_for_variant = -1;         // the override the plan was cut for
+    int shape_variant = 6;              // kernel shape the plan was cut for (the automatic choice resolved)
+    int rows_per_chunk = 32;            // 32, or 64 / 128 for regular short-row matrices
 };
 
 struct HostPipe;  // spmv.cu: streams / events / row blocks of the pipelined host-pointer product

@@ -24,7 +24,8 @@
 
 namespace g4s {
 
-constexpr int CHUNK_ROWS = 32;
+constexpr int CHUNK_ROWS = 32;       // rows per chunk for ordinary matrices (one row per lane)
+constexpr int MAX_CHUNK_ROWS = 128;  // regular short-row matrices pack up to 4 passes of 32 rows into a chunk
 
 // ------------------------------------------------------------------------------------------------------
 // small device-wide exclusive scan (int32), three launches; also used by SpGEMM for C's row pointers
@@ -157,7 +158,7 @@ int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, lo
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Inspector.  One thread walks one block of 32 consecutive rows and cuts it greedily:
+// Inspector.  One thread walks one block of `block_rows` (32, 64 or 128) consecutive rows and cuts it greedily:
 //   - rows are appended to the open chunk while its nonzeros stay <= cap;
 //   - a row longer than cap closes the open chunk and becomes ceil(len/cap) single-piece chunks.
 // Pass 1 counts chunks per block, a scan turns counts into offsets, pass 2 writes the descriptors.
@@ -185,16 +186,16 @@ struct ChunkWalk {
 };
 
 template <bool FILL>
-__global__ void chunk_walk_kernel(const int *__restrict__ rowptr, int rows, int cap, int nblocks,
+__global__ void chunk_walk_kernel(const int *__restrict__ rowptr, int rows, int cap, int block_rows, int nblocks,
                                   int *__restrict__ counts,            // !FILL: out, FILL: exclusive offsets in
                                   int2 *__restrict__ desc, unsigned char *__restrict__ lanes_lg,
                                   int4 *__restrict__ long_rows, int *__restrict__ n_long) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    const int r_begin = b * CHUNK_ROWS, r_end = min(r_begin + CHUNK_ROWS, rows);
+    const int r_begin = b * block_rows, r_end = min(r_begin + block_rows, rows);
     int out = FILL ? counts[b] : 0;
     int n = 0;
-    int len[CHUNK_ROWS];
+    int len[MAX_CHUNK_ROWS];
     int open_rows = 0, open_nnz = 0, open_row0 = r_begin;
     int prev = __ldg(rowptr + r_begin);
     auto close_open = [&]() {
@@ -621,6 +622,7 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
 }
 
 constexpr int SPMV_CAP = 1024;
+constexpr int G4S_SPMV_AUTO_REGULAR_SHORT = 15;  // short regular rows: 512-nnz chunks of up to 128 rows, 36 warps per SM
 constexpr int G4S_SPMV_AUTO_SHORT = 12;  // short-row matrices: 256-nnz chunks, 32 warps per SM, 128 KB left as L1
 void spmv_free_plan(g4s_csr *h);
 void spmv_free_host_pipe(g4s_csr *h);
@@ -644,34 +646,61 @@ static SpmvShape shape_of(int variant) {
         case 12: return {256, 1, 32, 1};
         case 13: return {256, 1, 32, 2};
         case 14: return {256, 1, 24, 2};
+        case 15: return {512, 1, 18, 2};
         default: return {1024, 1, 9, 2};
     }
 }
-// automatic choice: short-row matrices (32 rows never fill 512 nonzeros) take the small-buffer shape
-static int auto_variant(const g4s_csr *h) {
+// Automatic choice from the row-length statistics (profiles/r01_other_kernels_summary.md):
+//  * rows long enough that 32 of them fill a 1024-nnz chunk (27-point stencils): 1024-nnz chunks, 18 warps per SM;
+//  * short REGULAR rows (2-D 5-point: 32 rows are only 160 nonzeros, and the per-chunk latency dominates): 512-nnz
+//    chunks of up to 128 rows (several 32-row passes per chunk) and 36 warps per SM;
+//  * short SKEWED rows (power-law graphs): 256-nnz chunks, 32 warps per SM and 128 KB left as L1 for the x gathers.
+struct SpmvConfig {
+    int variant, rows_per_chunk;
+};
+static SpmvConfig choose_config(const g4s_csr *h, int forced_variant, int max_row_len) {
     const double avg = h->rows ? (double)h->nnz / h->rows : 0.0;
-    return avg * CHUNK_ROWS <= 512.0 ? G4S_SPMV_AUTO_SHORT : 6;
+    const bool regular = max_row_len <= 4.0 * avg + 8.0;
+    int variant = forced_variant;
+    if (!variant) variant = avg * CHUNK_ROWS > 512.0 ? 6 : (regular ? G4S_SPMV_AUTO_REGULAR_SHORT : G4S_SPMV_AUTO_SHORT);
+    int rpc = CHUNK_ROWS;
+    if (regular) {
+        const int cap = shape_of(variant).cap;
+        while (rpc < MAX_CHUNK_ROWS && avg * (2 * rpc) <= (double)cap) rpc *= 2;
+    }
+    return {variant, rpc};
 }
 
 int spmv_build_plan(g4s_csr *h, cudaStream_t stream) {
     SpmvPlan &p = h->plan;
-    const int want_cap = shape_of(p.variant ? p.variant : auto_variant(h)).cap;
-    if (p.desc && p.cap == want_cap) return G4S_OK;
-    if (p.desc) {  // the tuning variant changed the chunk size: cut the rows again
+    if (p.desc && p.built_for_variant == p.variant) return G4S_OK;
+    if (p.desc) {  // the tuning variant changed: cut the rows again
         spmv_free_host_pipe(h);
         spmv_free_plan(h);
     }
-    p.cap = want_cap;
-    const int nblocks = (h->rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
     int *counts = nullptr, *stats = nullptr;
-    G4S_CUDA(cudaMalloc(&counts, sizeof(int) * ((size_t)nblocks + 1)));
     G4S_CUDA(cudaMalloc(&stats, sizeof(int) * 4));
+    G4S_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, stream));
+    count_long_rows_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->rows, 0x7fffffff, stats, stats + 1);
+    G4S_CHECK_LAUNCH("count_long_rows_kernel");
+    int hmax[2] = {0, 0};
+    G4S_CUDA(cudaMemcpyAsync(hmax, stats, sizeof(hmax), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaStreamSynchronize(stream));
+    const SpmvConfig cfg = choose_config(h, p.variant, hmax[1]);
+    p.built_for_variant = p.variant;
+    p.shape_variant = cfg.variant;
+    p.rows_per_chunk = cfg.rows_per_chunk;
+    const int want_cap = shape_of(cfg.variant).cap;
+    const int block_rows = cfg.rows_per_chunk;
+    p.cap = want_cap;
+    const int nblocks = (h->rows + block_rows - 1) / block_rows;
+    G4S_CUDA(cudaMalloc(&counts, sizeof(int) * ((size_t)nblocks + 1)));
     G4S_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, stream));
     const int threads = 128;
     count_long_rows_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->rows, p.cap, stats, stats + 1);
     G4S_CHECK_LAUNCH("count_long_rows_kernel");
     chunk_walk_kernel<false><<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(
-        h->rowptr, h->rows, p.cap, nblocks, counts, nullptr, nullptr, nullptr, nullptr);
+        h->rowptr, h->rows, p.cap, block_rows, nblocks, counts, nullptr, nullptr, nullptr, nullptr);
     G4S_CHECK_LAUNCH("chunk_walk_kernel<count>");
     long long total = 0;
     int rc = exclusive_scan_i32(counts, counts, nblocks, 0, &total, stream);
@@ -689,7 +718,7 @@ int spmv_build_plan(g4s_csr *h, cudaStream_t stream) {
     G4S_CUDA(cudaMemsetAsync(p.carry, 0, sizeof(double) * (size_t)std::max(p.nchunks, 1), stream));
     G4S_CUDA(cudaMemsetAsync(stats + 2, 0, sizeof(int), stream));
     chunk_walk_kernel<true><<<(nblocks + threads - 1) / threads, threads, 0, stream>>>(
-        h->rowptr, h->rows, p.cap, nblocks, counts, p.desc, p.lanes_lg, p.long_rows, stats + 2);
+        h->rowptr, h->rows, p.cap, block_rows, nblocks, counts, p.desc, p.lanes_lg, p.long_rows, stats + 2);
     G4S_CHECK_LAUNCH("chunk_walk_kernel<fill>");
     write_sentinel_kernel<<<1, 1, 0, stream>>>(p.desc, p.nchunks, h->rows, h->rowptr);
     G4S_CHECK_LAUNCH("write_sentinel_kernel");
@@ -718,7 +747,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     const SpmvPlan &p = h->plan;
-    if (p.variant == 9) {  // comparison baseline
+    if (p.variant == 9) {  // comparison baseline (the plan is unused)
         if (accum || row_map || parts) return fail(G4S_ERR_INVALID, "warp-per-row baseline supports plain y = A x only");
         spmv_warp_row_kernel<<<sm_count() * 8, 256, 0, stream>>>(h->rowptr, h->colids, h->values, x, y, h->rows);
         G4S_CHECK_LAUNCH("spmv_warp_row_kernel");
@@ -750,7 +779,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     // r01_other_kernels_summary.md).  27-nnz stencil rows: 1024-nnz chunks, 18 single-buffered warps per SM as 2 CTAs
     // of 9 (deeper per-warp rings with fewer warps lose: resident warps hide the latency).  Short or power-law rows
     // (mean row length <= 16): 256-nnz chunks, 32 warps per SM and the rest of shared memory left to L1.
-    const int variant = parts ? 6 : (p.variant ? p.variant : auto_variant(h));
+    const int variant = parts ? 6 : p.shape_variant;
     switch (variant) {
         case 1: rc = launch_chunk_kernel<1024, 1, 16>(a, accum, 1, stream); break;
         case 2: rc = launch_chunk_kernel<1024, 2, 8>(a, accum, 1, stream); break;
@@ -764,6 +793,7 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
         case 12: rc = launch_chunk_kernel<256, 1, 32>(a, accum, 1, stream); break;
         case 13: rc = launch_chunk_kernel<256, 1, 32>(a, accum, 2, stream); break;
         case 14: rc = launch_chunk_kernel<256, 1, 24>(a, accum, 2, stream); break;
+        case 15: rc = launch_chunk_kernel<512, 1, 18>(a, accum, 2, stream); break;
         default: rc = launch_chunk_kernel<1024, 1, 9>(a, accum, 2, stream, parts); break;
     }
     if (rc) return rc;

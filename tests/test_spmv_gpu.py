@@ -84,10 +84,10 @@ def test_spmv_every_lane_width(g4s, oracle, lanes):
         check_spmv(g4s, oracle, A, rng.uniform(-1, 1, A[1]), lanes=lanes)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15])
 def test_spmv_every_kernel_variant(g4s, oracle, variant):
     rng = np.random.default_rng(variant)
-    for A in (laplacian_3d_27(16), powerlaw_csr(20000, 6)):
+    for A in (laplacian_3d_27(16), powerlaw_csr(20000, 6), laplacian_2d(70)):  # 2-D: several 32-row passes per chunk
         check_spmv(g4s, oracle, A, rng.uniform(-1, 1, A[1]), variant=variant)
 
 
