@@ -241,6 +241,25 @@ int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, con
                                        const double *bvalues_dev, int world, const double *const *B_parts,
                                        const int *cuts, double *C_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * The G4S graph engine ABI.  `spmm_dense` is the engine CitcomS calls through E->spmm_dense
+ * (citcoms/bin/Citcom.c:45-48,93; citcoms/lib/global_defs.h:48-49,854-857); the reference declares it but does not
+ * ship its body.  Semantics per GraphProcess (deepmd/source/op/graph.h:21-32): for every vertex, gather() for each of
+ * its `degree` neighbours, then apply().  The callbacks are host functions, so this entry runs on the CPU by
+ * construction; elapsed seconds are added to *time.
+ * g4s_ebe_matvec_device is the callback-free device form of the engine's one concrete instance, CitcomS's
+ * element-by-element operator (gather at citcoms/lib/Element_calculations.c:453-471): Au[dofs[e][r]] +=
+ * sum_c elt_k[e][r*ndof + c] * u[dofs[e][c]] for every element e; ndof = 24 / 8 / 4 (loc_mat_size); Au is accumulated
+ * into (the caller zeroes it, as e_assemble_del2_u does at Element_calculations.c:494-495).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef void (*g4s_fun_gather)(int, int, const double **, const double *, double *);
+typedef void (*g4s_fun_apply)(int, const double **, const double *, double *);
+void spmm_dense(uint32_t numNodes, uint32_t degree, const double **edgeWeight, const double *vertexStates,
+                double *temp, double *result, g4s_fun_gather gather, g4s_fun_apply apply, double *time,
+                int threadNum);
+int g4s_ebe_matvec_device(int nel, int ndof, const double *elt_k_dev, const int *elem_dofs_dev, const double *u_dev,
+                          double *Au_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,15 @@ class Oracle:
                                           _ip(colids), _dp(values))
         return (row1 - row0, n ** 3, rowptr, colids, values)
 
+    def ebe_matvec(self, elt_k, elem_dofs, u, neq, ends=8, dims=3):
+        """CitcomS element-by-element operator (gather at Element_calculations.c:453-471), flattened dof map."""
+        elt_k, u = _f64(elt_k), _f64(u)
+        elem_dofs = _i32(elem_dofs)
+        nel = elem_dofs.shape[0]
+        Au = np.zeros(neq, dtype=np.float64)
+        self.lib.oracle_ebe_matvec(C.c_int(nel), C.c_int(ends), C.c_int(dims), _dp(elt_k), _ip(elem_dofs), _dp(u), _dp(Au))
+        return Au
+
     def dense_mv(self, name, A, B):
         """name in dgemv|dsymv|dtrmv|dspmv; returns (B_after, C) like mv/mv.c's (A,B,C,dim) calls."""
         A = _f64(A).reshape(-1)

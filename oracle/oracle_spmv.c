@@ -158,3 +158,40 @@ void oracle_gen_laplacian3d27(int n, long long row0, long long row1, int *rowptr
                 }
     }
 }
+
+/* The G4S engine loop, GraphProcess (deepmd/source/op/graph.h:21-32): for every vertex, gather() per neighbour, then
+ * apply().  Restated sequentially; the reference's copy runs it under `omp parallel for schedule(dynamic,1)`. */
+typedef void (*oracle_gather_fn)(int, int, const double **, const double *, double *);
+typedef void (*oracle_apply_fn)(int, const double **, const double *, double *);
+void oracle_graph_process(int num_nodes, int degree, const double **edge_weight, const double *states, double *result,
+                          oracle_gather_fn gather, oracle_apply_fn apply) {
+    for (int vi = 0; vi < num_nodes; ++vi) {
+        for (int nb = 0; nb < degree; ++nb) gather(vi, nb, edge_weight, states, result);
+        if (apply) apply(vi, edge_weight, states, result);
+    }
+}
+
+/* CitcomS's gather callback (citcoms/lib/Element_calculations.c:453-471) summed over a whole mesh, i.e. what
+ * e_assemble_del2_u computes through the engine (:475-510): for element e, node a, direction i,
+ *     Au[dof(e,a,i)] += sum_b sum_j elt_k[e][ii + j] * u[dof(e,b,j)],   ii = (a*n+b)*dims - (dims*n+dims) + (i-1)*n
+ * (1-based a, b, i; n = loc_mat_size = ends*dims), which is row 3(a-1)+(i-1), columns 3(b-1)+j of a row-major n x n
+ * block.  The IEN / ID indirection is flattened into elem_dofs[e][3(a-1)+(i-1)].  PARITY UNPINNED: CitcomS is not
+ * buildable here; the index arithmetic is restated literally and cross-checked against an assembled sparse matrix. */
+void oracle_ebe_matvec(int nel, int ends, int dims, const double *elt_k, const int *elem_dofs, const double *u,
+                       double *Au) {
+    const int n = ends * dims;
+    for (int e = 0; e < nel; ++e) {
+        const double *k = elt_k + (size_t)e * n * n;
+        const int *dof = elem_dofs + (size_t)e * n;
+        for (int a = 1; a <= ends; ++a)
+            for (int i = 1; i <= dims; ++i) {
+                const int aa = dof[dims * (a - 1) + (i - 1)];
+                for (int b = 1; b <= ends; ++b) {
+                    const int ii = (a * n + b) * dims - (dims * n + dims) + (i - 1) * n;
+                    double s = 0.0;
+                    for (int j = 0; j < dims; ++j) s += k[ii + j] * u[dof[dims * (b - 1) + j]];
+                    Au[aa] += s;
+                }
+            }
+    }
+}
