@@ -436,7 +436,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_GRID, help="grid edge (default 400 = BASELINE configs[1])")
+    ap.add_argument("--grid", dest="n", type=int, default=N_GRID, help="grid edge (default 400 = BASELINE configs[1])")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline budget at N=1")
     ap.add_argument("--mode", default="peer", choices=["peer", "halo", "allgather", "auto"],
                     help="multi-GPU x assembly (N > 1)")

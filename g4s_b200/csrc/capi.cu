@@ -379,6 +379,18 @@ int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *
                                 (cudaStream_t)stream);
 }
 
+int g4s_spmv_partition_info(g4s_csr_t A, int *n_remote_columns, unsigned *owner_mask) {
+    if (!A) return fail(G4S_ERR_INVALID, "null handle");
+    if (n_remote_columns) *n_remote_columns = A->localized ? A->plan.part_n_needed : -1;
+    if (owner_mask) *owner_mask = A->plan.part_owner_mask;
+    return G4S_OK;
+}
+int g4s_spmv_partition_set_wait_mask(g4s_csr_t A, unsigned mask) {
+    if (!A) return fail(G4S_ERR_INVALID, "null handle");
+    A->plan.part_owner_mask = mask;
+    return G4S_OK;
+}
+
 int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch, void *stream) {
     if (!flag_arrays) return fail(G4S_ERR_INVALID, "g4s_peer_signal: null argument");
     int rc = ensure_device();

@@ -44,6 +44,12 @@ struct SpmvPlan {
     double *carry = nullptr;            // [nchunks]   partial sums of non-final pieces of long rows
     int4 *long_rows = nullptr;          // [n_long]    (row, first chunk, pieces, -)
     unsigned char *part_flags = nullptr;  // [nchunks] partitioned x: chunk references a remote column
+    int *part_needed = nullptr;           // localized handle: global column of halo entry k (ascending)
+    int part_n_needed = 0;
+    double *part_halo = nullptr;          // [part_n_needed] remote x entries, refilled by every partitioned product
+    unsigned long long *part_halo_done = nullptr;  // gather warps that have published their share, over all products
+    unsigned long long part_products = 0;
+    unsigned part_owner_mask = 0xffu;     // ranks that own this rank's remote columns
     int part_lo = 0, part_hi = 0;       // owned column range the flags were computed for
     int n_long = 0;                     // rows longer than cap
     int max_row_len = 0;
@@ -65,6 +71,7 @@ struct g4s_csr {
     int *colids = nullptr;
     double *values = nullptr;
     bool owns = false;
+    bool localized = false;  // column ids outside the owned range were rewritten to -1 - k by a partitioned product
     int sorted_cols = -1;  // -1 unknown, 1 every row's column ids strictly ascending, 0 not (SpGEMM merge class)
     bool pooled = false;  // arrays came from cudaMallocAsync (stream-ordered pool) rather than cudaMalloc
     g4s::SpmvPlan plan;

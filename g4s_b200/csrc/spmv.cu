@@ -296,6 +296,16 @@ struct XParts {
     unsigned long long epoch;
     unsigned long long *signal[MAX_PARTS];  // every rank's flag array (peer-mapped), or null: the caller signals
     int self;
+    // in-kernel halo pull (localized handles): the first gather_ctas CTAs copy the remote x entries this rank needs
+    // (needed[k] = global column of halo[k]) into local memory, then count themselves into halo_done; column ids of
+    // remote entries were rewritten to -1 - k, so chunks never touch NVLink themselves
+    const int *needed;
+    int n_needed;
+    double *halo;
+    unsigned long long *halo_done;
+    unsigned long long halo_target;
+    int gather_ctas;
+    unsigned owner_mask;  // ranks whose flags this rank waits for (the owners of its remote columns; all if unknown)
 };
 __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
     if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
@@ -331,7 +341,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 // warp-collective: lane q waits until rank q has published this product's epoch.  Ten seconds without progress
 // means a peer died: trap, so that the failure is loud instead of a silent hang.
 __device__ __forceinline__ void wait_peers(const XParts &xp, int lane) {
-    if (lane < xp.world) {
+    if (lane < xp.world && ((xp.owner_mask >> lane) & 1u)) {
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while (ld_acquire_sys_u64(xp.flags + lane) < xp.epoch) {
@@ -359,6 +369,39 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
     constexpr int PER_PASS = 32 / L;
     const int g = lane / L, sub = lane % L;
     const double *__restrict__ x = a.x;
+    if (PART && xp.halo) {
+        // Localized handle: remote entries carry column -1 - k and read halo[k], which the gather CTAs filled from the
+        // owners' memory earlier in this launch (ld.global.cg: the halo was written by other SMs during this kernel).
+        const double *halo = xp.halo;
+        for (int base = 0; base < nloc; base += PER_PASS) {
+            const int r = base + g;
+            int s = 0, e = 0;
+            if (r < nloc) {
+                if (base) {
+                    rp0 = __ldg(a.rowptr + row0 + r);
+                    rp1 = __ldg(a.rowptr + row0 + r + 1);
+                }
+                s = max(rp0, nnz0);
+                e = min(rp1, nnz1);
+            }
+            double acc = 0.0;
+            int k = s + sub - a0;
+            const int ke = e - a0;
+#pragma unroll 4
+            for (; k < ke; k += L) {
+                const int c = buf.cols[k];
+                const double xv = c >= 0 ? __ldg(x + c) : __ldcg(halo + (-1 - c));
+                acc = fma(buf.vals[k], xv, acc);
+            }
+#pragma unroll
+            for (int o = L >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (sub == 0 && r < nloc) {
+                if (R > 0) a.y[row0 + r] = acc;
+                else a.carry[chunk] = acc;
+            }
+        }
+        return;
+    }
     if (PART) {
         // A chunk that touches another GPU's slice: NVLink loads cost microseconds, so they are not chained into
         // the row sums.  First every staged value is multiplied by its x entry, 32 consecutive nonzeros per step
@@ -444,7 +487,15 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
     // phases of the sweep, to de-synchronise the NVLink-bound chunks at the ends of a rank's range, was measured:
     // 8 bands cost more in x re-reads — 0.42 -> 0.52 ms on 8 M rows — than the de-synchronisation gains.)
     const int nit = wglobal < a.nchunks ? (int)(((long long)a.nchunks - wglobal + stride - 1) / stride) : 0;
-    auto chunk_at = [&](int i) -> long long { return (long long)wglobal + (long long)i * stride; };
+    // with an in-kernel halo every warp starts in the MIDDLE of its list and wraps around: the chunks that need the
+    // halo sit at the two ends of a rank's range, so they come up half a kernel after the gather CTAs started, and
+    // the whole grid still sweeps one band of rows at a time
+    const int rot = (PART && xp.halo) ? nit / 2 : 0;
+    auto chunk_at = [&](int i) -> long long {
+        int k = i + rot;
+        if (k >= nit) k -= nit;
+        return (long long)wglobal + (long long)k * stride;
+    };
     if (PART && xp.flags && xp.signal[0] && blockIdx.x == 0 && warp == 0 && lane < xp.world) {
         // publish this rank's slice for this product (it was written before the launch): a release store of the epoch
         // into every rank's flag array, slot self — the separate signal launch is folded into the product
@@ -465,6 +516,28 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
     __syncwarp();
 
     bool peers_ready = !PART || xp.flags == nullptr;
+    bool halo_ready = !(PART && xp.halo);
+    if (PART && xp.halo && (int)blockIdx.x < xp.gather_ctas) {
+        // halo pull: wait for the owners, then copy the needed remote entries with 8 independent NVLink loads in
+        // flight per lane, publish them device-wide and count this warp in
+        if (!peers_ready) {
+            wait_peers(xp, lane);
+            peers_ready = true;
+        }
+        const int gstride = xp.gather_ctas * WARPS * 32;
+        int k = (blockIdx.x * WARPS + warp) * 32 + lane;
+        for (; k + 7 * gstride < xp.n_needed; k += 8 * gstride) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = *x_part_ptr(xp, __ldg(xp.needed + k + u * gstride));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xp.halo[k + u * gstride] = v[u];
+        }
+        for (; k < xp.n_needed; k += gstride) xp.halo[k] = *x_part_ptr(xp, __ldg(xp.needed + k));
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(xp.halo_done, 1ULL);
+    }
     for (int it = 0; it < nit; ++it) {
         const long long c = chunk_at(it);
         const int b = it % NBUF;
@@ -492,7 +565,21 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         // partitioned x: only chunks that reference a remote column pay for the owner lookup; every other chunk
         // runs the plain code on the GPU's own slice (a.x = own slice rebased to global column ids)
         const bool remote = PART && (code & 0x80);
-        if (PART && remote && !peers_ready) {  // only chunks that touch another GPU's slice ever wait
+        if (PART && remote && xp.halo) {
+            if (!halo_ready) {  // the gather CTAs have published the whole halo for this product
+                if (lane == 0) {
+                    unsigned long long t0, t1, seen;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(xp.halo_done) : "memory");
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 10000000000ULL) __trap();
+                    } while (seen < xp.halo_target);
+                }
+                __syncwarp();
+                halo_ready = true;
+            }
+        } else if (PART && remote && !peers_ready) {  // only chunks that touch another GPU's slice ever wait
             wait_peers(xp, lane);
             peers_ready = true;
         }
@@ -514,7 +601,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
     }
     // one warp per GPU always observes every rank's flag before the kernel ends, even when no chunk was remote:
     // a rank can then never run two products ahead of a peer that still reads its double-buffered slice
-    if (PART && !peers_ready && blockIdx.x == 0 && warp == 0) wait_peers(xp, lane);
+    if (PART && !peers_ready && blockIdx.x == 0 && warp == 0 && xp.flags) wait_peers(xp, lane);
 }
 
 struct FlagPtrs {
@@ -535,6 +622,26 @@ int peer_signal(unsigned long long *const *flag_arrays, int world, int self, uns
     peer_signal_kernel<<<1, 32, 0, stream>>>(f, world, self, epoch);
     G4S_CHECK_LAUNCH("peer_signal_kernel");
     return G4S_OK;
+}
+
+// Localization of a rank's row block for the in-kernel halo pull: columns outside [lo, hi) are numbered in ascending
+// order (needed[k]) and their ids rewritten to -1 - k.
+__global__ void localize_flag_kernel(const int *__restrict__ colids, long long nnz, int lo, int hi, int *__restrict__ flags) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
+        const int c = __ldg(colids + k);
+        if (c < lo || c >= hi) flags[c] = 1;
+    }
+}
+__global__ void localize_list_kernel(const int *__restrict__ flags, const int *__restrict__ pos, int cols,
+                                     int *__restrict__ needed) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cols && flags[c]) needed[pos[c]] = c;
+}
+__global__ void localize_rewrite_kernel(int *__restrict__ colids, long long nnz, int lo, int hi, const int *__restrict__ pos) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
+        const int c = colids[k];
+        if (c < lo || c >= hi) colids[k] = -1 - pos[c];
+    }
 }
 
 // one warp per chunk: does it reference a column outside [lo, hi)?
@@ -614,6 +721,13 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     none.epoch = 0;
     none.self = 0;
     for (int q = 0; q < MAX_PARTS; ++q) none.signal[q] = nullptr;
+    none.needed = nullptr;
+    none.n_needed = 0;
+    none.halo = nullptr;
+    none.halo_done = nullptr;
+    none.halo_target = 0;
+    none.gather_ctas = 0;
+    none.owner_mask = 0xffu;
     if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
     else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
     else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
@@ -735,6 +849,9 @@ void spmv_free_plan(g4s_csr *h) {
     if (p.carry) cudaFree(p.carry);
     if (p.long_rows) cudaFree(p.long_rows);
     if (p.part_flags) cudaFree(p.part_flags);
+    if (p.part_needed) cudaFree(p.part_needed);
+    if (p.part_halo) cudaFree(p.part_halo);
+    if (p.part_halo_done) cudaFree(p.part_halo_done);
     const int lanes = p.lanes_per_row, variant = p.variant;
     p = SpmvPlan();
     p.lanes_per_row = lanes;
@@ -744,6 +861,8 @@ void spmv_free_plan(g4s_csr *h) {
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
              const XParts *parts, int chunk_begin, int chunk_end) {
     if (h->rows == 0) return G4S_OK;
+    if (h->localized && !parts)
+        return fail(G4S_ERR_INVALID, "this handle's column ids were localized by a partitioned product; use g4s_spmv_partitioned_device");
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     const SpmvPlan &p = h->plan;
@@ -823,6 +942,52 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     SpmvPlan &p = h->plan;
+    if (h->localized && (p.part_lo != xp.lo || p.part_hi != xp.hi))
+        return fail(G4S_ERR_INVALID, "partitioned SpMV: the handle was localized for another column range");
+    if (!p.part_flags && h->owns && !h->localized && world > 1) {
+        // first partitioned product on an owned handle: number the remote columns and rewrite their ids (once)
+        const int cols = h->cols, grid = sm_count() * 8;
+        int *flags = nullptr, *pos = nullptr;
+        G4S_CUDA(cudaMalloc(&flags, sizeof(int) * ((size_t)cols + 1)));
+        G4S_CUDA(cudaMalloc(&pos, sizeof(int) * ((size_t)cols + 1)));
+        G4S_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)cols + 1), stream));
+        if (h->nnz) {
+            localize_flag_kernel<<<grid, 256, 0, stream>>>(h->colids, h->nnz, xp.lo, xp.hi, flags);
+            G4S_CHECK_LAUNCH("localize_flag_kernel");
+        }
+        long long nn = 0;
+        if ((rc = exclusive_scan_i32(flags, pos, cols, 0, &nn, stream))) return rc;
+        p.part_n_needed = (int)nn;
+        G4S_CUDA(cudaMalloc(&p.part_needed, sizeof(int) * (size_t)std::max<long long>(nn, 1)));
+        G4S_CUDA(cudaMalloc(&p.part_halo, sizeof(double) * (size_t)std::max<long long>(nn, 1)));
+        G4S_CUDA(cudaMalloc(&p.part_halo_done, sizeof(unsigned long long)));
+        G4S_CUDA(cudaMemsetAsync(p.part_halo_done, 0, sizeof(unsigned long long), stream));
+        if (cols) {
+            localize_list_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(flags, pos, cols, p.part_needed);
+            G4S_CHECK_LAUNCH("localize_list_kernel");
+        }
+        if (h->nnz) {
+            localize_rewrite_kernel<<<grid, 256, 0, stream>>>(h->colids, h->nnz, xp.lo, xp.hi, pos);
+            G4S_CHECK_LAUNCH("localize_rewrite_kernel");
+        }
+        G4S_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(flags);
+        cudaFree(pos);
+        h->localized = true;
+        p.part_products = 0;
+        // which ranks own those columns: a product only has to wait for them (for a stencil: the two neighbours),
+        // not for all ranks of the box
+        p.part_owner_mask = 0;
+        if (nn > 0) {
+            std::vector<int> hn((size_t)nn);
+            G4S_CUDA(cudaMemcpy(hn.data(), p.part_needed, sizeof(int) * (size_t)nn, cudaMemcpyDeviceToHost));
+            int q = 0;
+            for (long long k = 0; k < nn; ++k) {  // needed is ascending: walk the cuts once
+                while (q + 1 < world && hn[k] >= cuts[q + 1]) ++q;
+                p.part_owner_mask |= 1u << q;
+            }
+        }
+    }
     if (!p.part_flags || p.part_lo != xp.lo || p.part_hi != xp.hi) {  // once per (matrix, owned range)
         if (!p.part_flags) G4S_CUDA(cudaMalloc(&p.part_flags, (size_t)p.nchunks + 1));
         if (p.nchunks) {
@@ -832,6 +997,25 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         }
         p.part_lo = xp.lo;
         p.part_hi = xp.hi;
+    }
+    xp.needed = nullptr;
+    xp.n_needed = 0;
+    xp.halo = nullptr;
+    xp.halo_done = nullptr;
+    xp.halo_target = 0;
+    xp.gather_ctas = 0;
+    xp.owner_mask = 0xffu;
+    if (h->localized) {
+        const long long want = ((long long)p.nchunks + 8) / 9;  // grid of the 1 x 9 x 2 shape (launch_chunk_kernel)
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 2));
+        xp.needed = p.part_needed;
+        xp.n_needed = p.part_n_needed;
+        xp.halo = p.part_halo;
+        xp.halo_done = p.part_halo_done;
+        xp.gather_ctas = std::min(grid, 16);
+        xp.owner_mask = p.part_owner_mask;
+        p.part_products += 1;  // the counter only grows: product n is complete at n * (gather warps)
+        xp.halo_target = p.part_products * (unsigned long long)xp.gather_ctas * 9ULL;
     }
     // the plain path indexes x by global column id: rebase the own slice (never dereferenced outside [lo, hi))
     return spmv_run(h, x_parts[self] - xp.lo, y, nullptr, false, stream, &xp, 0, -1);

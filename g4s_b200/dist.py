@@ -212,6 +212,25 @@ class DistSpMV:
         self._k = 0
         self.n_halo, self.exchange_bytes, self.launches_per_step = 0, 0, 1
         dist.barrier(group=self.group)
+        # set-up product on zeros: numbers this rank's remote columns (the library rewrites their ids once) and tells
+        # which ranks own them.  A product then waits for those ranks only -- widened here to the ranks that read THIS
+        # rank's slice, so that the double-buffering argument also holds for patterns that are not symmetric.
+        for xb in self.x_buffers:
+            xb.zero_()
+        scratch = torch.empty(max(self.local_rows, 1), dtype=torch.float64, device=dev)
+        self.apply(self.x_buffers[0], scratch)
+        torch.cuda.synchronize()
+        n_remote, mask = C.c_int(), C.c_uint()
+        check(L.g4s_spmv_partition_info(self.A.handle, C.byref(n_remote), C.byref(mask)))
+        self.n_halo, self.exchange_bytes = max(n_remote.value, 0), 8 * max(n_remote.value, 0)
+        every_mask = [None] * self.world
+        dist.all_gather_object(every_mask, int(mask.value), group=self.group)
+        wait = int(mask.value)
+        for q in range(self.world):
+            if (every_mask[q] >> self.rank) & 1:
+                wait |= 1 << q
+        check(L.g4s_spmv_partition_set_wait_mask(self.A.handle, C.c_uint(wait)))
+        dist.barrier(group=self.group)
 
     def next_x(self):
         """peer mode: the shared buffer the next apply() will read; fill it in place to skip apply()'s copy."""

@@ -179,6 +179,12 @@ int g4s_csr_split_columns(g4s_csr_t A, int c0, int c1, g4s_csr_t *diag, g4s_csr_
 int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *const *x_parts, const int *cuts,
                                 double *y_dev, const unsigned long long *ready_flags_dev, unsigned long long epoch,
                                 unsigned long long *const *signal_arrays, void *stream);
+/* After the first partitioned product on an owned handle (which numbers the remote columns and rewrites their ids in
+ * place): how many x entries the rank pulls from peers per product (-1: handle not localized) and the bit mask of the
+ * ranks that own them.  A product waits for the flags of the ranks in the mask only; the caller widens it to the ranks
+ * that read ITS slice when the pattern is not structurally symmetric (g4s_b200/dist.py does, with one all-gather). */
+int g4s_spmv_partition_info(g4s_csr_t A, int *n_remote_columns, unsigned *owner_mask);
+int g4s_spmv_partition_set_wait_mask(g4s_csr_t A, unsigned mask);
 /* flag_arrays[q] = rank q's flag array (own or IPC-mapped).  Stream-ordered after the writes of the x slice:
  * stores `epoch` into slot `self` of every rank's array (release, system scope). */
 int g4s_peer_signal(unsigned long long *const *flag_arrays, int world, int self, unsigned long long epoch,
