@@ -74,14 +74,16 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
                                 const int *__restrict__ brpt, int M, int cols, int *__restrict__ row_work,
                                 unsigned long long *__restrict__ total, int *__restrict__ class_count,
                                 unsigned char *__restrict__ row_class, bool b_sorted) {
-    // class_count: [NCLASS] histogram, then [NCLASS] cursors (unused here), then [1] max work
+    // class_count: [NCLASS] histogram, then [NCLASS] cursors (unused here), then [1] max work; [4 * NCLASS + 1]: longest
+    // row of A in class 1 (sizes the merge kernel's list count)
     __shared__ int hist[NCLASS];
     __shared__ unsigned long long bsum;
-    __shared__ int bmax;
+    __shared__ int bmax, bmaxlen;
     if (threadIdx.x < NCLASS) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         bsum = 0;
         bmax = 0;
+        bmaxlen = 0;
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,10 +96,12 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
         const int wi = w > 2147483647LL ? 2147483647 : (int)w;
         if (row_work) row_work[i] = wi;
         if (class_count) {
-            const int cls = work_class(wi, cols, __ldg(arpt + i + 1) - __ldg(arpt + i), b_sorted);
+            const int alen = __ldg(arpt + i + 1) - __ldg(arpt + i);
+            const int cls = work_class(wi, cols, alen, b_sorted);
             row_class[i] = (unsigned char)cls;
             atomicAdd(&hist[cls], 1);
             if (wi) atomicMax(&bmax, wi);
+            if (cls == 1 && alen > bmaxlen) atomicMax(&bmaxlen, alen);
         }
     }
     unsigned long long s = (unsigned long long)w;
@@ -108,6 +112,7 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
     if (threadIdx.x == 0 && bsum) atomicAdd(total, bsum);
     if (class_count && threadIdx.x < NCLASS && hist[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
     if (class_count && threadIdx.x == 0 && bmax) atomicMax(&class_count[2 * NCLASS], bmax);
+    if (class_count && threadIdx.x == 0 && bmaxlen) atomicMax(&class_count[4 * NCLASS + 1], bmaxlen);
 }
 
 // rows of each class, ascending inside a block of 256 rows; blocks reserve their ranges with one atomic per class
@@ -468,10 +473,11 @@ __global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const Spgemm
 // accumulation order (j ascending over A's row, one entry of B's row per column; hash_mult.h:579-600), so the
 // values are bit-identical to HashSpGEMM<false,true> and the columns come out sorted with no sort at all.
 constexpr int MERGE_STAGE = 16;  // output entries per row staged in shared memory for the coalesced store
-template <bool NUMERIC>
+// K = lists per thread: the compare / fold code is unrolled per list, so rows of A with at most 5 entries (2-D 5-point
+// stencils) run a K = 5 instance (binning reports the longest class-1 row).
+template <int K, bool NUMERIC>
 __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
                                                                int nlist) {
-    constexpr int K = MERGE_MAX_A;
     constexpr int THREADS = 256;
     // numeric phase: [MERGE_STAGE][THREADS] columns and values; entry e of lane L sits in column (L + e) & 31 of its
     // warp's 32 columns, so that both the per-thread writes and the warp's read-back are bank-conflict-free
@@ -722,6 +728,7 @@ struct Bins {
     int offset[NCLASS + 1] = {0};
     long long total_work = 0;
     int max_work = 0;
+    int merge_lists = MERGE_MAX_A;  // longest row of A in class 1
 };
 
 static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab_keys, double *slab_vals,
@@ -730,8 +737,11 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
     auto list = [&](int c) -> const int * { return b.identity ? nullptr : b.perm + b.offset[c]; };
     if (b.count[1]) {
         const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
-        if (numeric) spgemm_merge_row_kernel<true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
-        else spgemm_merge_row_kernel<false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
+        if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else if (k5) spgemm_merge_row_kernel<5, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else spgemm_merge_row_kernel<MERGE_MAX_A, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
     }
     if ((rc = launch_thread_row<32, 128>(a, list(2), b.count[2], numeric, stream))) return rc;
@@ -837,11 +847,12 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
                                                        ws.row_class, B->sorted_cols == 1);
         G4S_CHECK_LAUNCH("row_work_kernel");
     }
-    G4S_CUDA(cudaMemcpyAsync(ws.hcount, dcount, sizeof(int) * (2 * NCLASS + 1), cudaMemcpyDeviceToHost, stream));
+    G4S_CUDA(cudaMemcpyAsync(ws.hcount, dcount, sizeof(int) * (4 * NCLASS + 2), cudaMemcpyDeviceToHost, stream));
     G4S_CUDA(cudaMemcpyAsync(ws.htotal, ws.dtotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     G4S_CUDA(cudaStreamSynchronize(stream));
     b.total_work = (long long)*ws.htotal;
     b.max_work = ws.hcount[2 * NCLASS];
+    b.merge_lists = ws.hcount[4 * NCLASS + 1];
     int cur[NCLASS];
     {
         int off = 0;
