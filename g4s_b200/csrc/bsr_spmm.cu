@@ -3,12 +3,14 @@
 // CitcomS's 3-dof node operator, citcoms/lib/Element_calculations.c:516-571); the oracle's restatement
 // (oracle/oracle_spmv.c: oracle_bsr_spmm) is the checker.
 //
-// Three kernels, one warp per block row:
+// Four kernels, one warp per block row:
 //   dmma   (bs = 3, ncol = 64): FP64 tensor cores, mma.sync.m8n8k4.f64 (DMMA.8x8x4 in SASS; tcgen05 has no FP64
 //          kind).  The product is taken transposed, C_I^T[64 x 3] = Bg^T[64 x 3nb] A_I^T[3nb x 3], so the dense
 //          64 columns fill the M = 8 side of eight tiles, the 3 block rows sit in N = 8 (3/8 used) and the
 //          blocks of the row are packed back to back along K (3nb, four at a time).
 //   fma    (bs = 3, ncol = 64): plain DFMA, each lane owns two columns of the 64 (128-bit loads of B).
+//   kpack  (bs = 3, ncol = 64): DFMA with the row's scalar columns dealt to four lane groups (a third of the broadcast
+//          loads of block values); the single-GPU default.
 //   generic (any bs <= 8, any ncol): lane-per-column DFMA.
 // Which of dmma / fma is faster is a measured property of the part (profiles/): the default follows it.
 #include <algorithm>
@@ -17,7 +19,7 @@
 
 namespace g4s {
 
-static int g_bsr_variant = 0;  // 0 auto, 1 fma, 2 dmma, 3 generic
+static int g_bsr_variant = 0;  // 0 auto, 1 fma, 2 dmma, 3 generic, 4 K-packed fma
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -153,6 +155,109 @@ __global__ void __launch_bounds__(256) bsr3_spmm64_fma_parts_kernel(int mb, cons
     }
 }
 
+// K-packed DFMA kernel (bs = 3, ncol = 64), the single-GPU default.  ncu on the kernel above shows the LSU register
+// WRITEBACK (128 B per cycle per SM) 75-80 % busy, and most of it is the block values: a warp-uniform LDG.64 still writes
+// 8 bytes into each of 32 lanes, so the 9 broadcast values of a block cost 18 writeback cycles against 12 for the 1536
+// bytes of B the block really needs (32 data-pipe wavefronts per block measured; 64-bit instead of 128-bit loads of B
+// change nothing, profiles/r01_other_kernels_summary.md).  Here the row's blocks are read as one flat list of scalar
+// columns kk = 3 p + s (K of the product C_I = A_I[3 x K] Bg[K x 64]); lane group g = lane / 8 takes kk = g (mod 4),
+// so a lane needs only the THREE values A[0..2][kk] of its own column (3 LDG.64 per step of four columns instead of
+// 9 per block) and the 64 entries of row kk of Bg are split over the group's 8 lanes (columns 16 i + 2 j, +1 for
+// i = 0..3: every LDG.128 of a group is one 128-byte line).  Each lane accumulates 3 x 8 partial sums over its share
+// of K; the four groups are summed once per block row with a halving exchange (36 shuffles), after which lane
+// (g, j) holds C_I[0..2][16 g + 2 j, +1] and the warp stores three contiguous 512-byte rows.  Two steps are kept in
+// flight (120 registers, 16 warps per SM).  Measured: 20.3 data-pipe wavefronts per block instead of 32.2.
+template <bool PARTS>
+__global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const int *__restrict__ browptr,
+                                                                   const int *__restrict__ bcolids,
+                                                                   const double *__restrict__ bvalues,
+                                                                   const double *__restrict__ B, const BParts bp,
+                                                                   double *__restrict__ C) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+        const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        double2 acc[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][i] = make_double2(0.0, 0.0);
+        // this lane's scalar column: block p, column s of the block; a step of 4 columns is one block and one column on
+        int p = p0 + (g == 3 ? 1 : 0), s = g == 3 ? 0 : g;
+        int Jn = p < p1 ? __ldg(bcolids + p) : 0;
+        struct Step {
+            double a0, a1, a2;
+            double2 b[4];
+        };
+        // issues the loads of this lane's current column, moves on by four columns and fetches the next column id;
+        // returns whether any lane of the warp had a column left (warp-uniform)
+        auto load = [&](Step &st) -> bool {
+            const bool valid = p < p1;
+            const double *blk = bvalues + (size_t)p * 9 + s;
+            const double *brow = (PARTS ? b_part_row(bp, Jn) : B + (size_t)Jn * 192) + s * 64 + 2 * j;
+            st.a0 = st.a1 = st.a2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st.b[i] = make_double2(0.0, 0.0);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st.b[i] = __ldg(reinterpret_cast<const double2 *>(brow + 16 * i));
+                st.a0 = __ldg(blk);
+                st.a1 = __ldg(blk + 3);
+                st.a2 = __ldg(blk + 6);
+            }
+            ++p;
+            ++s;
+            if (s >= 3) {
+                s -= 3;
+                ++p;
+            }
+            Jn = p < p1 ? __ldg(bcolids + p) : 0;
+            return __any_sync(FULL, valid);
+        };
+        auto mac = [&](const Step &st) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[0][i].x = fma(st.a0, st.b[i].x, acc[0][i].x); acc[0][i].y = fma(st.a0, st.b[i].y, acc[0][i].y);
+                acc[1][i].x = fma(st.a1, st.b[i].x, acc[1][i].x); acc[1][i].y = fma(st.a1, st.b[i].y, acc[1][i].y);
+                acc[2][i].x = fma(st.a2, st.b[i].x, acc[2][i].x); acc[2][i].y = fma(st.a2, st.b[i].y, acc[2][i].y);
+            }
+        };
+        // two steps in flight: the loads of the next step are issued before the multiply-adds of the current one
+        Step sa, sb;
+        bool more = load(sa);
+        while (more) {
+            const bool more_b = load(sb);
+            mac(sa);
+            if (!more_b) break;
+            more = load(sa);
+            mac(sb);
+        }
+        // sum the four K groups: exchange halves with lane ^ 16, then with lane ^ 8; lane (g, j) ends with chunk i = g
+        const bool hi = (g & 2) != 0, lo = (g & 1) != 0;
+        double2 f[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double2 t[2];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii) {
+                const double2 send = hi ? acc[r][ii] : acc[r][ii + 2];
+                const double2 keep = hi ? acc[r][ii + 2] : acc[r][ii];
+                t[ii].x = keep.x + __shfl_xor_sync(FULL, send.x, 16);
+                t[ii].y = keep.y + __shfl_xor_sync(FULL, send.y, 16);
+            }
+            const double2 send = lo ? t[0] : t[1];
+            const double2 keep = lo ? t[1] : t[0];
+            f[r].x = keep.x + __shfl_xor_sync(FULL, send.x, 8);
+            f[r].y = keep.y + __shfl_xor_sync(FULL, send.y, 8);
+        }
+        double2 *c = reinterpret_cast<double2 *>(C + (size_t)I * 192) + lane;
+        c[0] = f[0];
+        c[32] = f[1];
+        c[64] = f[2];
+    }
+}
+
 template <int BS>
 __global__ void __launch_bounds__(256) bsr_spmm_generic_kernel(int mb, const int *__restrict__ browptr,
                                                                const int *__restrict__ bcolids,
@@ -194,7 +299,8 @@ using namespace g4s;
 extern "C" {
 
 int g4s_bsr_spmm_set_variant(int variant) {
-    if (variant < 0 || variant > 3) return fail(G4S_ERR_INVALID, "variant must be 0 (auto), 1 (fma), 2 (dmma) or 3 (generic)");
+    if (variant < 0 || variant > 4)
+        return fail(G4S_ERR_INVALID, "variant must be 0 (auto), 1 (fma), 2 (dmma), 3 (generic) or 4 (K-packed fma)");
     g_bsr_variant = variant;
     return G4S_OK;
 }
@@ -212,9 +318,13 @@ int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, con
     for (int q = 0; q <= 8; ++q) bp.cut[q] = cuts[q < world ? q : world];
     bp.world = world;
     const int grid = (int)std::min<long long>(((long long)mb_local * 32 + 255) / 256, (long long)sm_count() * 16);
-    bsr3_spmm64_fma_parts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev, bvalues_dev, bp,
-                                                                       C_dev);
-    G4S_CHECK_LAUNCH("bsr3_spmm64_fma_parts_kernel");
+    if (g_bsr_variant == 4)  // opt-in until it has been timed over NVLink: the plain DFMA kernel is the measured default
+        bsr3_spmm64_kpack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev,
+                                                                             bvalues_dev, nullptr, bp, C_dev);
+    else
+        bsr3_spmm64_fma_parts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev, bvalues_dev,
+                                                                           bp, C_dev);
+    G4S_CHECK_LAUNCH("bsr3_spmm64 partitioned kernel");
     return G4S_OK;
 }
 
@@ -229,9 +339,12 @@ int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const in
     const int grid = (int)std::min<long long>(((long long)mb * 32 + 255) / 256, (long long)sm_count() * 16);
     int variant = g_bsr_variant;
     const bool fast_ok = bs == 3 && ncol == 64 && ((reinterpret_cast<uintptr_t>(B_dev) | reinterpret_cast<uintptr_t>(C_dev)) & 15) == 0;
-    if (variant == 0) variant = fast_ok ? 1 : 3;
-    if ((variant == 1 || variant == 2) && !fast_ok) variant = 3;
-    if (variant == 2) {
+    if (variant == 0) variant = fast_ok ? 4 : 3;
+    if (variant != 3 && !fast_ok) variant = 3;
+    if (variant == 4) {
+        BParts none = {};
+        bsr3_spmm64_kpack_kernel<false><<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, none, C_dev);
+    } else if (variant == 2) {
         bsr3_spmm64_dmma_kernel<<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, C_dev);
     } else if (variant == 1) {
         bsr3_spmm64_fma_kernel<<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, C_dev);

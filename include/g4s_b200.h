@@ -238,7 +238,7 @@ int g4s_csr_from_edges_device(long m, long n, const long *start_dev, const long 
  * ---------------------------------------------------------------------------------------------------- */
 int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const int *bcolids_dev,
                         const double *bvalues_dev, int ncol, const double *B_dev, double *C_dev, void *stream);
-/* kernel choice for bs = 3, ncol = 64: 0 automatic, 1 DFMA, 2 DMMA (FP64 tensor cores), 3 generic */
+/* kernel choice for bs = 3, ncol = 64: 0 automatic, 1 DFMA, 2 DMMA (FP64 tensor cores), 3 generic, 4 K-packed DFMA */
 int g4s_bsr_spmm_set_variant(int variant);
 /* Multi-GPU form for bs = 3, ncol = 64 (one NVSwitch box, world <= 8): this rank's mb_local block rows with GLOBAL block
  * column ids; B is row-partitioned by `cuts` (block rows) and B_parts[q] points at rank q's slice (own memory or

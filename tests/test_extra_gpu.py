@@ -125,7 +125,7 @@ def bsr_case(mb, density, bs, seed):
     return pat.indptr.astype(np.int32), pat.indices.astype(np.int32), blocks
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_bsr3_spmm64_matches_oracle(g4s, oracle, variant):
     import torch
 
