@@ -58,14 +58,39 @@ class CSR:
 
     # ---- constructors mirroring the reference ---------------------------------------------------------
     @classmethod
-    def construct(cls, filename):
-        """CSR::construct (mm/inc/CSR.h:485-669): MatrixMarket coordinate file -> CSR."""
+    def construct(cls, filename, cache=False):
+        """CSR::construct (mm/inc/CSR.h:485-669): MatrixMarket coordinate file -> CSR.  cache=True keeps / reuses the
+        binary twin `<filename>.g4scsr` (g4s_csr_read_cached); `self.cache_hit` tells which path ran."""
         rows, cols, nnz = C.c_int(), C.c_int(), C.c_int()
         rp, ci, va = i32p(), i32p(), f64p()
-        check(lib().g4s_csr_read_matrix_market(str(filename).encode(), C.byref(rows), C.byref(cols), C.byref(nnz),
-                                               C.byref(rp), C.byref(ci), C.byref(va)))
+        hit = C.c_int(0)
+        if cache:
+            check(lib().g4s_csr_read_cached(str(filename).encode(), C.byref(rows), C.byref(cols), C.byref(nnz),
+                                            C.byref(rp), C.byref(ci), C.byref(va), C.byref(hit)))
+        else:
+            check(lib().g4s_csr_read_matrix_market(str(filename).encode(), C.byref(rows), C.byref(cols), C.byref(nnz),
+                                                   C.byref(rp), C.byref(ci), C.byref(va)))
+        self = cls(rows.value, cols.value, _take(rp, rows.value + 1, np.int32), _take(ci, nnz.value, np.int32),
+                   _take(va, nnz.value, np.float64))
+        self.cache_hit = bool(hit.value)
+        return self
+
+    @classmethod
+    def load_binary(cls, filename):
+        """Binary CSR cache file (g4s_csr_read_binary) -> CSR."""
+        rows, cols, nnz = C.c_int(), C.c_int(), C.c_int()
+        rp, ci, va = i32p(), i32p(), f64p()
+        check(lib().g4s_csr_read_binary(str(filename).encode(), C.byref(rows), C.byref(cols), C.byref(nnz),
+                                        C.byref(rp), C.byref(ci), C.byref(va)))
         return cls(rows.value, cols.value, _take(rp, rows.value + 1, np.int32), _take(ci, nnz.value, np.int32),
                    _take(va, nnz.value, np.float64))
+
+    def save_binary(self, filename):
+        """CSR -> binary cache file (g4s_csr_write_binary)."""
+        if self.rowptr is None:
+            self.to_host()
+        check(lib().g4s_csr_write_binary(str(filename).encode(), C.c_int(self.rows), C.c_int(self.cols),
+                                         C.c_int(len(self.colids)), _ip(self.rowptr), _ip(self.colids), _dp(self.values)))
 
     @classmethod
     def from_graph(cls, n, start, end, w):

@@ -36,9 +36,14 @@ void die(const char *what) {
     std::fprintf(stderr, "g4s_spgemm: %s failed: %s\n", what, g4s_last_error());
     std::exit(1);
 }
+// construct() through the binary cache `<path>.g4scsr` (G4S_NO_CACHE=1: parse the text file every time, as the reference)
 void construct(Csr &m, const std::string &path) {
-    if (g4s_csr_read_matrix_market(path.c_str(), &m.rows, &m.cols, &m.nnz, &m.rowptr, &m.colids, &m.values) != G4S_OK)
-        die(("construct(" + path + ")").c_str());
+    int hit = 0;
+    const int rc = std::getenv("G4S_NO_CACHE")
+                       ? g4s_csr_read_matrix_market(path.c_str(), &m.rows, &m.cols, &m.nnz, &m.rowptr, &m.colids, &m.values)
+                       : g4s_csr_read_cached(path.c_str(), &m.rows, &m.cols, &m.nnz, &m.rowptr, &m.colids, &m.values, &hit);
+    if (rc != G4S_OK) die(("construct(" + path + ")").c_str());
+    if (hit) std::printf("(loaded from %s.g4scsr)\n", path.c_str());
 }
 void trim(Csr &m, int M_, int N_) {
     Csr t;

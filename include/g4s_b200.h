@@ -205,6 +205,17 @@ int g4s_device_free(void *p);
  * ---------------------------------------------------------------------------------------------------- */
 int g4s_csr_read_matrix_market(const char *path, int *rows, int *cols, int *nnz, int **rowptr, int **colids,
                                double **values);
+/* Binary CSR cache (no counterpart in the reference, whose construct() re-parses the text file with
+ * `ifstream >>` on every run, mm/inc/CSR.h:526-553): a 64-byte header (magic "G4SCSR1", shape, checksum) followed by the
+ * int32 rowptr / colids and fp64 values exactly as construct() produced them.  read_binary validates magic, sizes, row
+ * pointers and checksum and returns G4S_ERR_FORMAT for anything else.  read_cached is the drop-in for construct(): it
+ * loads `<mtx_path>.g4scsr` when that file exists and is not older than the text file, otherwise parses the text file
+ * and (best effort) writes the cache; *cache_hit (optional) reports which happened. */
+int g4s_csr_write_binary(const char *path, int rows, int cols, int nnz, const int *rowptr, const int *colids,
+                         const double *values);
+int g4s_csr_read_binary(const char *path, int *rows, int *cols, int *nnz, int **rowptr, int **colids, double **values);
+int g4s_csr_read_cached(const char *mtx_path, int *rows, int *cols, int *nnz, int **rowptr, int **colids, double **values,
+                        int *cache_hit);
 /* edge list laid out as class graph (mm/inc/graph.h:4-25): long start[m], end[m]; double w[m]; n vertices */
 int g4s_csr_from_edge_list(long m, long n, const long *start, const long *end, const double *w, int *nnz,
                            int **rowptr, int **colids, double **values);
