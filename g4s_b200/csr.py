@@ -283,3 +283,21 @@ def mkl(A, B, timing=None):
                         C.byref(cnnz), C.byref(t)))
     return CSR(a.rows, b.cols, _take(rp, a.rows + 1, np.int32), _take(ci, cnnz.value, np.int32),
                _take(va, cnnz.value, np.float64))
+
+
+def bsr_from_citcoms_nodes(node_map, eqn_k1, eqn_k2, eqn_k3):
+    """CitcomS half-stored node format (Node_map, Eqn_k1..3; citcoms/lib/Construct_arrays.c:264-312) -> full BSR 3x3:
+    returns (browptr, bcolids, blocks[nnzb, 3, 3]).  float32 coefficients (the reference's higher_precision) or float64."""
+    node_map = _i32(node_map)
+    nno = len(node_map) // 42
+    dt = np.float32 if np.asarray(eqn_k1).dtype == np.float32 else np.float64
+    ks = [np.ascontiguousarray(k, dtype=dt) for k in (eqn_k1, eqn_k2, eqn_k3)]
+    if len(node_map) != nno * 42 or any(len(k) != nno * 42 for k in ks):
+        raise ValueError("node_map and Eqn_k1..3 must have nno*42 entries")
+    nnzb = C.c_int()
+    rp, ci, va = i32p(), i32p(), f64p()
+    check(lib().g4s_bsr_from_citcoms_nodes(C.c_int(nno), _ip(node_map), ks[0].ctypes.data_as(C.c_void_p),
+                                           ks[1].ctypes.data_as(C.c_void_p), ks[2].ctypes.data_as(C.c_void_p),
+                                           C.c_int(ks[0].itemsize), C.byref(nnzb), C.byref(rp), C.byref(ci), C.byref(va)))
+    return (_take(rp, nno + 1, np.int32), _take(ci, nnzb.value, np.int32),
+            _take(va, 9 * nnzb.value, np.float64).reshape(-1, 3, 3))

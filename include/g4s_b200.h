@@ -249,6 +249,15 @@ int g4s_csr_from_edges_device(long m, long n, const long *start_dev, const long 
  * ---------------------------------------------------------------------------------------------------- */
 int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const int *bcolids_dev,
                         const double *bvalues_dev, int ncol, const double *B_dev, double *C_dev, void *stream);
+/* CitcomS's assembled stiffness operator -> BSR 3x3, host.  Input is the reference's half-stored
+ * node format: node_map[nno*42] (construct_node_maps, citcoms/lib/Construct_arrays.c:264-310) and the coefficient arrays
+ * Eqn_k1/2/3[nno*42] (construct_node_ks, :330-456; value_bytes = 4 for the reference's `higher_precision` float,
+ * global_defs.h:116-120, or 8 for double).  Output (malloc'd, g4s_free): both triangles of the symmetric matrix as
+ * nno block rows sorted by block column, fp64 row-major 3x3 blocks, such that g4s_bsr_spmm_device applies the operator
+ * of n_assemble_del2_u (citcoms/lib/Element_calculations.c:516-565).  G4S_ERR_FORMAT for a map that is not in that
+ * format (a node not owning equations 3(node-1)+d, a slot that is not a lower-numbered node, a neighbour listed twice). */
+int g4s_bsr_from_citcoms_nodes(int nno, const int *node_map, const void *eqn_k1, const void *eqn_k2, const void *eqn_k3,
+                               int value_bytes, int *nnzb, int **browptr, int **bcolids, double **bvalues);
 /* kernel choice for bs = 3, ncol = 64: 0 automatic, 1 DFMA, 2 DMMA (FP64 tensor cores), 3 generic, 4 K-packed DFMA */
 int g4s_bsr_spmm_set_variant(int variant);
 /* Multi-GPU form for bs = 3, ncol = 64 (one NVSwitch box, world <= 8): this rank's mb_local block rows with GLOBAL block

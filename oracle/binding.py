@@ -108,6 +108,33 @@ class Oracle:
         self.lib.oracle_ebe_matvec(C.c_int(nel), C.c_int(ends), C.c_int(dims), _dp(elt_k), _ip(elem_dofs), _dp(u), _dp(Au))
         return Au
 
+    def citcoms_mesh(self, nox, noy, noz, elt_k):
+        """CitcomS node format of a structured hex mesh: (ien [nel,8] 1-based, node_map [nno*42], k1, k2, k3 float32
+        [nno*42]) from per-element 24x24 matrices, restating construct_ien / construct_node_maps / construct_node_ks."""
+        nno, nel = nox * noy * noz, (nox - 1) * (noy - 1) * (noz - 1)
+        ien = np.zeros((nel, 8), dtype=np.int32)
+        assert self.lib.oracle_citcoms_ien(C.c_int(nox), C.c_int(noy), C.c_int(noz), _ip(ien)) == nel
+        node_map = np.zeros(nno * 42, dtype=np.int32)
+        self.lib.oracle_citcoms_node_maps(C.c_int(nox), C.c_int(noy), C.c_int(noz), _ip(node_map))
+        elt_k = _f64(elt_k)
+        ks = [np.zeros(nno * 42, dtype=np.float32) for _ in range(3)]
+        fp = C.POINTER(C.c_float)
+        rc = self.lib.oracle_citcoms_node_ks(C.c_int(nel), C.c_int(nno), _ip(ien), _dp(elt_k), _ip(node_map),
+                                             ks[0].ctypes.data_as(fp), ks[1].ctypes.data_as(fp), ks[2].ctypes.data_as(fp))
+        assert rc == 0, "construct_node_ks: slot not found"
+        return ien, node_map, ks[0], ks[1], ks[2]
+
+    def citcoms_n_assemble_del2_u(self, node_map, k1, k2, k3, u):
+        """n_assemble_del2_u (citcoms/lib/Element_calculations.c:516-565): Au = K u on the half-stored node format."""
+        nno = len(node_map) // 42
+        fp = C.POINTER(C.c_float)
+        uu = np.zeros(3 * nno + 1, dtype=np.float64)
+        uu[:3 * nno] = u
+        Au = np.zeros(3 * nno + 1, dtype=np.float64)
+        self.lib.oracle_citcoms_n_assemble_del2_u(C.c_int(nno), _ip(_i32(node_map)), k1.ctypes.data_as(fp),
+                                                  k2.ctypes.data_as(fp), k3.ctypes.data_as(fp), _dp(uu), _dp(Au))
+        return Au[:3 * nno]
+
     def dense_mv(self, name, A, B):
         """name in dgemv|dsymv|dtrmv|dspmv; returns (B_after, C) like mv/mv.c's (A,B,C,dim) calls."""
         A = _f64(A).reshape(-1)

@@ -37,6 +37,14 @@ void oracle_gen_laplacian3d27(int n, long long row0, long long row1, int *rowptr
 void oracle_bsr_spmm(int mb, int bs, const int *browptr, const int *bcolids, const double *bvalues, int ncol,
                      const double *B, double *C);
 
+/* ---- oracle_citcoms.c: CitcomS node-format operator, PARITY UNPINNED ---- */
+int oracle_citcoms_ien(int nox, int noy, int noz, int *ien);
+void oracle_citcoms_node_maps(int nox, int noy, int noz, int *node_map);
+int oracle_citcoms_node_ks(int nel, int nno, const int *ien, const double *elt_k, const int *node_map, float *k1,
+                           float *k2, float *k3);
+void oracle_citcoms_n_assemble_del2_u(int nno, const int *node_map, const float *k1, const float *k2, const float *k3,
+                                      double *u, double *Au);
+
 /* ---- oracle_spgemm.c ---- */
 long long oracle_intprod(const int *arpt, const int *acol, const int *brpt, int rows, int *row_nz);
 void oracle_rows_offset(const int *row_nz, int rows, long long total_intprod, int parts, int *rows_offset);
