@@ -14,6 +14,7 @@
 //   generic (any bs <= 8, any ncol): lane-per-column DFMA.
 // Which of dmma / fma is faster is a measured property of the part (profiles/): the default follows it.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -122,6 +123,14 @@ __device__ __forceinline__ const double *b_part_row(const BParts &bp, int J) {
     }
     return b + (size_t)(J - cut) * 3 * 64;
 }
+// the same lookup for a block column that differs from lane to lane (K-packed kernels): count the cuts at or below J and
+// index the parameter block with the result (two constant-bank loads) instead of carrying a pointer through seven selects
+__device__ __forceinline__ const double *b_part_row_lane(const BParts &bp, int J) {
+    int owner = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) owner += (i < bp.world && J >= bp.cut[i]) ? 1 : 0;
+    return bp.base[owner] + (size_t)(J - bp.cut[owner]) * 3 * 64;
+}
 __global__ void __launch_bounds__(256) bsr3_spmm64_fma_parts_kernel(int mb, const int *__restrict__ browptr,
                                                                     const int *__restrict__ bcolids,
                                                                     const double *__restrict__ bvalues,
@@ -167,17 +176,56 @@ __global__ void __launch_bounds__(256) bsr3_spmm64_fma_parts_kernel(int mb, cons
 // of K; the four groups are summed once per block row with a halving exchange (36 shuffles), after which lane
 // (g, j) holds C_I[0..2][16 g + 2 j, +1] and the warp stores three contiguous 512-byte rows.  Two steps are kept in
 // flight (120 registers, 16 warps per SM).  Measured: 20.3 data-pipe wavefronts per block instead of 32.2.
-template <bool PARTS>
-__global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const int *__restrict__ browptr,
-                                                                   const int *__restrict__ bcolids,
-                                                                   const double *__restrict__ bvalues,
-                                                                   const double *__restrict__ B, const BParts bp,
-                                                                   double *__restrict__ C) {
+// loads that do not allocate in L1 (block values and column ids are used once; L1 is kept for the rows of B)
+template <bool STREAM>
+__device__ __forceinline__ double kpack_ld_a(const double *p) {
+    if (!STREAM) return __ldg(p);
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <bool STREAM>
+__device__ __forceinline__ int kpack_ld_j(const int *p) {
+    if (!STREAM) return __ldg(p);
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Asks for the block values and column ids of block row `In` (the row this warp takes next) ahead of time: they are a
+// DRAM stream that is used exactly once, so without this every step of the row waits a full DRAM latency for them.
+// One prefetch instruction covers 32 lines of 128 bytes.  level 1: into L2, 2: into L1.
+__device__ __forceinline__ void kpack_prefetch_row(int level, int pn0, int pn1, const int *bcolids, const double *bvalues) {
+    const int lane = threadIdx.x & 31;
+    const char *v0 = reinterpret_cast<const char *>(bvalues + (size_t)pn0 * 9);
+    const char *v1 = reinterpret_cast<const char *>(bvalues + (size_t)pn1 * 9);
+    const char *c0 = reinterpret_cast<const char *>(bcolids + pn0);
+    const char *c1 = reinterpret_cast<const char *>(bcolids + pn1);
+    for (const char *q = v0 + 128 * lane; q < v1; q += 128 * 32) {
+        if (level == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+    for (const char *q = c0 + 128 * lane; q < c1; q += 128 * 32) {
+        if (level == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+}
+
+// one block row I by one warp; In = the row the warp takes next (or -1), prefetched at level pf
+template <bool PARTS, bool STREAM>
+__device__ __forceinline__ void kpack_row(int I, int In, int pf, const int *__restrict__ browptr,
+                                          const int *__restrict__ bcolids, const double *__restrict__ bvalues,
+                                          const double *__restrict__ B, const BParts &bp, double *__restrict__ C) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
-    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += (gridDim.x * blockDim.x) >> 5) {
+    {
         const int p0 = __ldg(browptr + I), p1 = __ldg(browptr + I + 1);
+        int pn0 = 0, pn1 = 0;
+        if (pf && In >= 0) {
+            pn0 = __ldg(browptr + In);
+            pn1 = __ldg(browptr + In + 1);
+        }
         double2 acc[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -185,7 +233,7 @@ __global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const
             for (int i = 0; i < 4; ++i) acc[r][i] = make_double2(0.0, 0.0);
         // this lane's scalar column: block p, column s of the block; a step of 4 columns is one block and one column on
         int p = p0 + (g == 3 ? 1 : 0), s = g == 3 ? 0 : g;
-        int Jn = p < p1 ? __ldg(bcolids + p) : 0;
+        int Jn = p < p1 ? kpack_ld_j<STREAM>(bcolids + p) : 0;
         struct Step {
             double a0, a1, a2;
             double2 b[4];
@@ -195,16 +243,16 @@ __global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const
         auto load = [&](Step &st) -> bool {
             const bool valid = p < p1;
             const double *blk = bvalues + (size_t)p * 9 + s;
-            const double *brow = (PARTS ? b_part_row(bp, Jn) : B + (size_t)Jn * 192) + s * 64 + 2 * j;
+            const double *brow = (PARTS ? b_part_row_lane(bp, Jn) : B + (size_t)Jn * 192) + s * 64 + 2 * j;
             st.a0 = st.a1 = st.a2 = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) st.b[i] = make_double2(0.0, 0.0);
             if (valid) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) st.b[i] = __ldg(reinterpret_cast<const double2 *>(brow + 16 * i));
-                st.a0 = __ldg(blk);
-                st.a1 = __ldg(blk + 3);
-                st.a2 = __ldg(blk + 6);
+                st.a0 = kpack_ld_a<STREAM>(blk);
+                st.a1 = kpack_ld_a<STREAM>(blk + 3);
+                st.a2 = kpack_ld_a<STREAM>(blk + 6);
             }
             ++p;
             ++s;
@@ -212,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const
                 s -= 3;
                 ++p;
             }
-            Jn = p < p1 ? __ldg(bcolids + p) : 0;
+            Jn = p < p1 ? kpack_ld_j<STREAM>(bcolids + p) : 0;
             return __any_sync(FULL, valid);
         };
         auto mac = [&](const Step &st) {
@@ -226,6 +274,7 @@ __global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const
         // two steps in flight: the loads of the next step are issued before the multiply-adds of the current one
         Step sa, sb;
         bool more = load(sa);
+        if (pf && In >= 0) kpack_prefetch_row(pf, pn0, pn1, bcolids, bvalues);
         while (more) {
             const bool more_b = load(sb);
             mac(sa);
@@ -258,6 +307,52 @@ __global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const
     }
 }
 
+template <bool PARTS>
+__global__ void __launch_bounds__(256, 2) bsr3_spmm64_kpack_kernel(int mb, const int *__restrict__ browptr,
+                                                                   const int *__restrict__ bcolids,
+                                                                   const double *__restrict__ bvalues,
+                                                                   const double *__restrict__ B,
+                                                                   const __grid_constant__ BParts bp,
+                                                                   double *__restrict__ C, int pf) {
+    const int stride = (gridDim.x * blockDim.x) >> 5;
+    for (int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; I < mb; I += stride)
+        kpack_row<PARTS, false>(I, I + stride < mb ? I + stride : -1, pf, browptr, bcolids, bvalues, B, bp, C);
+}
+
+// Ordered form: block rows are taken in the order the caller gives (row_order, a permutation of 0..mb-1), cut into TILES
+// (tile_ptr); one CTA of 16 warps per SM takes tiles blockIdx, blockIdx + grid, ... and works through a tile 16 entries
+// (one per warp) at a time.  With the tile-major order of g4s_grid_pencil_order (a 4 x 4 patch of mesh nodes swept along
+// the third axis = one tile) the 16 rows in flight on an SM share their rows of B, which then live in that SM's L1 (no
+// shared memory is used: the carve-out is all L1) instead of being fetched from L2 once per mesh line; neighbouring
+// pencils are swept by other SMs at the same time, so the halo rows they share are in L2 when the second SM asks.
+// Block values and column ids bypass L1 and are prefetched one row ahead.
+template <bool PARTS>
+__global__ void __launch_bounds__(512, 1) bsr3_spmm64_kpack_ordered_kernel(int mb, const int *__restrict__ row_order,
+                                                                           const int *__restrict__ tile_ptr, int ntiles,
+                                                                           const int *__restrict__ browptr,
+                                                                           const int *__restrict__ bcolids,
+                                                                           const double *__restrict__ bvalues,
+                                                                           const double *__restrict__ B,
+                                                                           const __grid_constant__ BParts bp,
+                                                                           double *__restrict__ C, int pf) {
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long r0, r1;
+        if (tile_ptr) {
+            r0 = __ldg(tile_ptr + t);
+            r1 = __ldg(tile_ptr + t + 1);
+        } else {  // no tiles given: one contiguous stretch of the order per CTA
+            const long long per = ((long long)mb + ntiles - 1) / ntiles;
+            r0 = per * t;
+            r1 = r0 + per < mb ? r0 + per : mb;
+        }
+        for (long long idx = r0 + warp; idx < r1; idx += wpc) {
+            const int In = idx + wpc < r1 ? __ldg(row_order + idx + wpc) : -1;
+            kpack_row<PARTS, true>(__ldg(row_order + idx), In, pf, browptr, bcolids, bvalues, B, bp, C);
+        }
+    }
+}
+
 template <int BS>
 __global__ void __launch_bounds__(256) bsr_spmm_generic_kernel(int mb, const int *__restrict__ browptr,
                                                                const int *__restrict__ bcolids,
@@ -286,6 +381,15 @@ __global__ void __launch_bounds__(256) bsr_spmm_generic_kernel(int mb, const int
     }
 }
 
+// prefetch level of the K-packed kernels (G4S_BSR_PF overrides: 0 none, 1 L2, 2 L1)
+static int kpack_pf() {
+    static const int v = [] {
+        const char *e = getenv("G4S_BSR_PF");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
 template <int BS>
 static void launch_generic(int grid, cudaStream_t st, int mb, const int *rp, const int *ci, const double *va, int ncol,
                            const double *B, double *C) {
@@ -305,26 +409,96 @@ int g4s_bsr_spmm_set_variant(int variant) {
     return G4S_OK;
 }
 
-int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, const int *bcolids_dev,
-                                       const double *bvalues_dev, int world, const double *const *B_parts,
-                                       const int *cuts, double *C_dev, void *stream) {
+static int partitioned_args(int mb_local, const int *browptr_dev, const double *const *B_parts, const int *cuts,
+                            double *C_dev, int world, BParts &bp) {
     if (mb_local < 0 || !browptr_dev || !B_parts || !cuts || !C_dev || world < 1 || world > 8)
-        return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_partitioned_device: bad arguments (1 <= world <= 8)");
-    if (mb_local == 0) return G4S_OK;
-    int rc = ensure_device();
-    if (rc) return rc;
-    BParts bp;
+        return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_partitioned: bad arguments (1 <= world <= 8)");
     for (int q = 0; q < 8; ++q) bp.base[q] = q < world ? B_parts[q] : nullptr;
     for (int q = 0; q <= 8; ++q) bp.cut[q] = cuts[q < world ? q : world];
     bp.world = world;
+    return G4S_OK;
+}
+
+int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, const int *bcolids_dev,
+                                       const double *bvalues_dev, int world, const double *const *B_parts,
+                                       const int *cuts, double *C_dev, void *stream) {
+    BParts bp;
+    int rc = partitioned_args(mb_local, browptr_dev, B_parts, cuts, C_dev, world, bp);
+    if (rc) return rc;
+    if (mb_local == 0) return G4S_OK;
+    if ((rc = ensure_device())) return rc;
     const int grid = (int)std::min<long long>(((long long)mb_local * 32 + 255) / 256, (long long)sm_count() * 16);
-    if (g_bsr_variant == 4)  // opt-in until it has been timed over NVLink: the plain DFMA kernel is the measured default
+    if (g_bsr_variant == 4)  // K-packed kernel: opt-in here (g4s_bsr_spmm_set_variant(4)); plain DFMA is the measured default
         bsr3_spmm64_kpack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev,
-                                                                             bvalues_dev, nullptr, bp, C_dev);
+                                                                             bvalues_dev, nullptr, bp, C_dev, kpack_pf());
     else
         bsr3_spmm64_fma_parts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mb_local, browptr_dev, bcolids_dev, bvalues_dev,
                                                                            bp, C_dev);
     G4S_CHECK_LAUNCH("bsr3_spmm64 partitioned kernel");
+    return G4S_OK;
+}
+
+int g4s_bsr3_spmm64_partitioned_ordered_device(int mb_local, const int *browptr_dev, const int *bcolids_dev,
+                                               const double *bvalues_dev, int world, const double *const *B_parts,
+                                               const int *cuts, double *C_dev, const int *row_order_dev, void *stream) {
+    BParts bp;
+    int rc = partitioned_args(mb_local, browptr_dev, B_parts, cuts, C_dev, world, bp);
+    if (rc) return rc;
+    if (!row_order_dev) return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_partitioned_ordered_device: null row order");
+    if (mb_local == 0) return G4S_OK;
+    if ((rc = ensure_device())) return rc;
+    auto k = bsr3_spmm64_kpack_ordered_kernel<true>;
+    static bool configured = false;
+    if (!configured) {
+        G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+        configured = true;
+    }
+    const int grid = (int)std::min<long long>(((long long)mb_local + 15) / 16, (long long)sm_count());
+    k<<<grid, 512, 0, (cudaStream_t)stream>>>(mb_local, row_order_dev, nullptr, grid, browptr_dev, bcolids_dev, bvalues_dev,
+                                              nullptr, bp, C_dev, kpack_pf());
+    G4S_CHECK_LAUNCH("bsr3_spmm64_kpack_ordered_kernel");
+    return G4S_OK;
+}
+
+int g4s_bsr3_spmm64_ordered_device(int mb, int kb, const int *browptr_dev, const int *bcolids_dev, const double *bvalues_dev,
+                                   const double *B_dev, double *C_dev, const int *row_order_dev, const int *tile_ptr_dev,
+                                   int ntiles, void *stream) {
+    if (mb < 0 || kb < 0 || !browptr_dev || !B_dev || !C_dev || !row_order_dev ||
+        ((reinterpret_cast<uintptr_t>(B_dev) | reinterpret_cast<uintptr_t>(C_dev)) & 15))
+        return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_ordered_device: bad arguments (B and C 16-byte aligned)");
+    if (mb == 0) return G4S_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    auto k = bsr3_spmm64_kpack_ordered_kernel<false>;
+    static bool configured = false;
+    if (!configured) {  // no shared memory: the whole carve-out is L1
+        G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+        configured = true;
+    }
+    if (tile_ptr_dev && ntiles < 1) return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_ordered_device: tile_ptr without tiles");
+    const int grid = (int)std::min<long long>(tile_ptr_dev ? ntiles : ((long long)mb + 15) / 16, (long long)sm_count());
+    BParts none = {};
+    k<<<grid, 512, 0, (cudaStream_t)stream>>>(mb, row_order_dev, tile_ptr_dev, tile_ptr_dev ? ntiles : grid, browptr_dev,
+                                              bcolids_dev, bvalues_dev, B_dev, none, C_dev, kpack_pf());
+    G4S_CHECK_LAUNCH("bsr3_spmm64_kpack_ordered_kernel");
+    return G4S_OK;
+}
+
+int g4s_grid_pencil_order(int n0, int n1, int n2, int p0, int p1, int *order, int *tile_ptr, int *ntiles) {
+    if (n0 < 1 || n1 < 1 || n2 < 1 || p0 < 1 || p1 < 1 || !order || (long long)n0 * n1 * n2 > 2147483647LL)
+        return fail(G4S_ERR_INVALID, "g4s_grid_pencil_order: bad arguments");
+    long long at = 0;
+    int t = 0;
+    for (int b1 = 0; b1 < n1; b1 += p1)
+        for (int b0 = 0; b0 < n0; b0 += p0) {
+            if (tile_ptr) tile_ptr[t] = (int)at;
+            ++t;
+            for (int k = 0; k < n2; ++k)
+                for (int j = b1; j < std::min(n1, b1 + p1); ++j)
+                    for (int i = b0; i < std::min(n0, b0 + p0); ++i) order[at++] = (int)(((long long)k * n1 + j) * n0 + i);
+        }
+    if (tile_ptr) tile_ptr[t] = (int)at;
+    if (ntiles) *ntiles = t;
     return G4S_OK;
 }
 
@@ -343,7 +517,8 @@ int g4s_bsr_spmm_device(int mb, int kb, int bs, const int *browptr_dev, const in
     if (variant != 3 && !fast_ok) variant = 3;
     if (variant == 4) {
         BParts none = {};
-        bsr3_spmm64_kpack_kernel<false><<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, none, C_dev);
+        bsr3_spmm64_kpack_kernel<false><<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, none, C_dev,
+                                                              kpack_pf());
     } else if (variant == 2) {
         bsr3_spmm64_dmma_kernel<<<grid, 256, 0, st>>>(mb, browptr_dev, bcolids_dev, bvalues_dev, B_dev, C_dev);
     } else if (variant == 1) {

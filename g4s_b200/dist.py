@@ -372,6 +372,19 @@ class DistSpGEMM:
 
 
 # ------------------------------------------------------------------------------------------------ BSR SpMM
+def grid_pencil_order_local(n0, n1, n2, row0, row1, p0=4, p1=4):
+    """Tile-major order (g4s_grid_pencil_order) of the rows [row0, row1) of an n0 x n1 x n2 grid, as LOCAL row numbers:
+    the schedule for one rank's slab of a row-partitioned mesh matrix."""
+    import numpy as np
+
+    k0, k1 = row0 // (n0 * n1), -(-row1 // (n0 * n1))
+    order = np.empty(n0 * n1 * (k1 - k0), dtype=np.int32)
+    check(lib().g4s_grid_pencil_order(C.c_int(n0), C.c_int(n1), C.c_int(k1 - k0), C.c_int(p0), C.c_int(p1),
+                                      order.ctypes.data_as(C.c_void_p), None, None))
+    local = order.astype(np.int64) + k0 * n0 * n1 - row0
+    return local[(local >= 0) & (local < row1 - row0)].astype(np.int32)
+
+
 class DistBsrSpMM:
     """C = A_bsr B (3x3 blocks, 64 dense columns) with block rows cut over the ranks of one NVSwitch box.
 
@@ -380,7 +393,8 @@ class DistBsrSpMM:
     straight over NVLink (g4s_bsr3_spmm64_partitioned_device).  No halo exchange and no replicated B: at the
     256^3-node size of BASELINE config 5, B is 25.8 GB and a replica per GPU would cost more than the matrix."""
 
-    def __init__(self, browptr, bcolids, bvalues, cuts, group=None):
+    def __init__(self, browptr, bcolids, bvalues, cuts, group=None, row_order=None):
+        self.row_order = row_order  # optional device int32 permutation of the local block rows (tile-major schedule)
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         if self.world > 8:
@@ -417,6 +431,13 @@ class DistBsrSpMM:
         writes to its slice of B with a 4-byte all-reduce on the current stream."""
         if sync:
             dist.all_reduce(self._flag, group=self.group)
+        if self.row_order is not None:
+            check(lib().g4s_bsr3_spmm64_partitioned_ordered_device(
+                C.c_int(self.mb), C.c_void_p(self.browptr.data_ptr()), C.c_void_p(self.bcolids.data_ptr()),
+                C.c_void_p(self.bvalues.data_ptr()), C.c_int(self.world), self._parts, self._cuts_c,
+                C.c_void_p(C_local.data_ptr()), C.c_void_p(self.row_order.data_ptr()),
+                _stream_ptr(torch.cuda.current_stream())))
+            return C_local
         check(lib().g4s_bsr3_spmm64_partitioned_device(
             C.c_int(self.mb), C.c_void_p(self.browptr.data_ptr()), C.c_void_p(self.bcolids.data_ptr()),
             C.c_void_p(self.bvalues.data_ptr()), C.c_int(self.world), self._parts, self._cuts_c,

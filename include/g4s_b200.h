@@ -223,6 +223,12 @@ int g4s_csr_from_edge_list(long m, long n, const long *start, const long *end, c
 int g4s_csr_submatrix(int rows, int cols, const int *rowptr, const int *colids, const double *values, int M_,
                       int N_, int M_start, int N_start, int *nnz, int **orpt, int **ocol, double **oval);
 
+/* the same with this rank's block rows taken in the order row_order_dev[0..mb_local) (local row numbers; see
+ * g4s_bsr3_spmm64_ordered_device) */
+int g4s_bsr3_spmm64_partitioned_ordered_device(int mb_local, const int *browptr_dev, const int *bcolids_dev,
+                                               const double *bvalues_dev, int world, const double *const *B_parts,
+                                               const int *cuts, double *C_dev, const int *row_order_dev, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Synthetic inputs of BASELINE.json's configs, generated directly in CSR on the device.
  * Natural ordering, row = (k*n + j)*n + i.   2-D 5-point: diag 4, off-diag -1.  3-D 27-point: diag 26,
@@ -260,6 +266,18 @@ int g4s_bsr_from_citcoms_nodes(int nno, const int *node_map, const void *eqn_k1,
                                int value_bytes, int *nnzb, int **browptr, int **bcolids, double **bvalues);
 /* kernel choice for bs = 3, ncol = 64: 0 automatic, 1 DFMA, 2 DMMA (FP64 tensor cores), 3 generic, 4 K-packed DFMA */
 int g4s_bsr_spmm_set_variant(int variant);
+/* Ordered form for bs = 3, ncol = 64: block rows are processed in the order row_order_dev[0..mb) (a permutation of the
+ * block rows; the result is the same C, only the schedule changes), cut into tiles [tile_ptr_dev[t], tile_ptr_dev[t+1])
+ * that are handed to the SMs round-robin (tile_ptr_dev may be null: one contiguous stretch of the order per SM).  With a
+ * tile-major order of a structured mesh the block rows in flight on one SM share their rows of B, which are then served
+ * by that SM's L1, and neighbouring tiles are in flight on other SMs at the same time. */
+int g4s_bsr3_spmm64_ordered_device(int mb, int kb, const int *browptr_dev, const int *bcolids_dev, const double *bvalues_dev,
+                                   const double *B_dev, double *C_dev, const int *row_order_dev, const int *tile_ptr_dev,
+                                   int ntiles, void *stream);
+/* Tile-major order of an n0 x n1 x n2 grid numbered n0 fastest (node = (k*n1 + j)*n0 + i): p0 x p1 patches of the first
+ * two axes, each swept along the third axis (one tile).  order (host) receives n0*n1*n2 node numbers; tile_ptr (host,
+ * optional) ceil(n0/p0)*ceil(n1/p1) + 1 offsets into it; *ntiles (optional) the number of tiles. */
+int g4s_grid_pencil_order(int n0, int n1, int n2, int p0, int p1, int *order, int *tile_ptr, int *ntiles);
 /* Multi-GPU form for bs = 3, ncol = 64 (one NVSwitch box, world <= 8): this rank's mb_local block rows with GLOBAL block
  * column ids; B is row-partitioned by `cuts` (block rows) and B_parts[q] points at rank q's slice (own memory or
  * CUDA-IPC peer memory, see g4s_peer_alloc): rows of B owned by other GPUs are read over NVLink inside the kernel. */

@@ -106,12 +106,20 @@ def main():
                      torch.from_numpy(blocks[s:e].reshape(-1)).cuda(), cuts)
     op.B_local.copy_(torch.from_numpy(Bd[c0 * 3:c1 * 3]).cuda())
     Cl = torch.empty((c1 - c0) * 3, 64, dtype=torch.float64, device="cuda")
-    op.apply(Cl)
-    torch.cuda.synchronize()
-    good = bool(np.allclose(Cl.cpu().numpy(), want[c0 * 3:c1 * 3], rtol=0, atol=1e-11))
-    if not good:
-        print("rank %d: dist bsr mismatch" % rank, flush=True)
-    ok = ok and good
+    import ctypes as C
+
+    for mode in ("dfma", "kpack", "ordered"):
+        Cl.fill_(-7.0)
+        g4s_b200.lib().g4s_bsr_spmm_set_variant(C.c_int(4 if mode == "kpack" else 0))
+        op.row_order = torch.from_numpy(np.random.default_rng(rank).permutation(c1 - c0).astype(np.int32)).cuda() \
+            if mode == "ordered" else None
+        op.apply(Cl)
+        torch.cuda.synchronize()
+        good = bool(np.allclose(Cl.cpu().numpy(), want[c0 * 3:c1 * 3], rtol=0, atol=1e-11))
+        if not good:
+            print("rank %d: dist bsr mismatch (%s)" % (rank, mode), flush=True)
+        ok = ok and good
+    g4s_b200.lib().g4s_bsr_spmm_set_variant(C.c_int(0))
     op.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -147,6 +147,40 @@ def test_bsr3_spmm64_matches_oracle(g4s, oracle, variant):
     assert np.all(np.abs(got - want) <= 1e-12 * absw + 1e-300)
 
 
+@pytest.mark.parametrize("order", ["random", "pencil"])
+def test_bsr3_spmm64_ordered_matches_oracle(g4s, oracle, order):
+    import torch
+
+    n0, n1, n2 = 7, 5, 6
+    mb, bs, ncol = n0 * n1 * n2, 3, 64
+    rp, ci, blocks = bsr_case(mb, 0.04, bs, 9)
+    Bd = np.random.default_rng(778).uniform(-1, 1, (mb * bs, ncol))
+    want = oracle.bsr_spmm(rp, ci, blocks.reshape(-1), bs, Bd)
+    absw = oracle.bsr_spmm(rp, ci, np.abs(blocks).reshape(-1), bs, np.abs(Bd))
+    L = g4s.lib()
+    tiles, nt = None, C.c_int(0)
+    if order == "random":
+        perm = np.random.default_rng(3).permutation(mb).astype(np.int32)
+    else:
+        perm = np.empty(mb, dtype=np.int32)
+        tiles = np.empty(2 * 2 + 1, dtype=np.int32)
+        g4s._lib.check(L.g4s_grid_pencil_order(C.c_int(n0), C.c_int(n1), C.c_int(n2), C.c_int(4), C.c_int(4),
+                                               perm.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p),
+                                               C.byref(nt)))
+        assert np.array_equal(np.sort(perm), np.arange(mb)) and nt.value == 4 and tiles[-1] == mb
+    t = [torch.from_numpy(a).cuda() for a in (rp, ci, blocks.reshape(-1), Bd.reshape(-1), perm)]
+    td = torch.from_numpy(tiles).cuda() if tiles is not None else None
+    out = torch.full((mb * bs * ncol,), -7.0, dtype=torch.float64, device="cuda")
+    g4s._lib.check(L.g4s_bsr3_spmm64_ordered_device(C.c_int(mb), C.c_int(mb), C.c_void_p(t[0].data_ptr()),
+                                                    C.c_void_p(t[1].data_ptr()), C.c_void_p(t[2].data_ptr()),
+                                                    C.c_void_p(t[3].data_ptr()), C.c_void_p(out.data_ptr()),
+                                                    C.c_void_p(t[4].data_ptr()),
+                                                    C.c_void_p(td.data_ptr() if td is not None else 0), nt, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(mb * bs, ncol)
+    assert np.all(np.abs(got - want) <= 1e-12 * absw + 1e-300)
+
+
 @pytest.mark.parametrize("bs,ncol", [(1, 5), (2, 33), (4, 64), (8, 7)])
 def test_bsr_generic_shapes(g4s, oracle, bs, ncol):
     import torch

@@ -181,3 +181,23 @@ def test_partitioner_matches_reference_cut(g4s, oracle):
     assert L.compute_flop_host(rp.ctypes.data_as(C.POINTER(C.c_int)),
                                np.ascontiguousarray(A[3]).ctypes.data_as(C.POINTER(C.c_int)),
                                rp.ctypes.data_as(C.POINTER(C.c_int)), C.c_int(A[0])) == total
+
+
+def test_grid_pencil_order_is_a_tile_major_permutation(g4s):
+    n0, n1, n2 = 6, 5, 3
+    order = np.empty(n0 * n1 * n2, dtype=np.int32)
+    tiles = np.empty(2 * 3 + 1, dtype=np.int32)
+    nt = C.c_int()
+    g4s._lib.check(g4s.lib().g4s_grid_pencil_order(C.c_int(n0), C.c_int(n1), C.c_int(n2), C.c_int(4), C.c_int(2),
+                                                   order.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p),
+                                                   C.byref(nt)))
+    assert np.array_equal(np.sort(order), np.arange(n0 * n1 * n2))
+    assert nt.value == 6 and list(tiles) == [0, 24, 36, 60, 72, 84, 90]
+    node = lambda i, j, k: (k * n1 + j) * n0 + i  # noqa: E731
+    # first pencil: patch i in [0,4), j in [0,2), swept along k
+    want = [node(i, j, k) for k in range(n2) for j in range(2) for i in range(4)]
+    assert list(order[:len(want)]) == want
+    # second pencil is the ragged rest of the first axis
+    assert list(order[len(want):len(want) + 4]) == [node(4, 0, 0), node(5, 0, 0), node(4, 1, 0), node(5, 1, 0)]
+    assert g4s.lib().g4s_grid_pencil_order(C.c_int(0), C.c_int(1), C.c_int(1), C.c_int(1), C.c_int(1),
+                                           order.ctypes.data_as(C.c_void_p), None, None) == -1

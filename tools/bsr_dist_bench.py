@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C  # noqa: E402
 
 import g4s_b200  # noqa: E402
-from g4s_b200.dist import DistBsrSpMM, _DevArray, partition_by_prefix  # noqa: E402
+from g4s_b200.dist import DistBsrSpMM, _DevArray, grid_pencil_order_local, partition_by_prefix  # noqa: E402
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -40,26 +40,35 @@ op = DistBsrSpMM(browptr, bcol, blocks, cuts)
 g = torch.Generator(device=dev).manual_seed(777 + rank)
 op.B_local.copy_(torch.rand(mb * 3, 64, dtype=torch.float64, device=dev, generator=g) * 2 - 1)
 Cl = torch.empty(mb * 3, 64, dtype=torch.float64, device=dev)
-for _ in range(2):
-    op.apply(Cl)
-dist.barrier()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters):
-    op.apply(Cl)
-e1.record()
-dist.barrier()
-torch.cuda.synchronize()
-t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
+order = torch.from_numpy(grid_pencil_order_local(n, n, n, cuts[rank], cuts[rank + 1])).to(dev)
 tot = torch.tensor([float(nb)], dtype=torch.float64, device=dev)
 dist.all_reduce(tot)
+results = {}
+for mode in ("dfma", "kpack", "ordered"):  # plain DFMA kernel, K-packed kernel, K-packed kernel in tile-major row order
+    L.g4s_bsr_spmm_set_variant(C.c_int(4 if mode == "kpack" else 1))
+    op.row_order = order if mode == "ordered" else None
+    for _ in range(2):
+        op.apply(Cl)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op.apply(Cl)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    results[mode] = (float(t.item()), float(Cl.double().sum().item()))
+L.g4s_bsr_spmm_set_variant(C.c_int(0))
 if rank == 0:
-    nbt, ms = float(tot.item()), float(t.item())
+    nbt = float(tot.item())
     nbytes = 76.0 * nbt + 4.0 * (rows + 1) + 2 * 8.0 * 3 * rows * 64
-    print(json.dumps({"workload": "BSR 3x3 SpMM x 64 cols, %d^3 nodes (BASELINE configs[4])" % n, "n_gpus": world,
-                      "blocks": nbt, "ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "tflops": 2 * 9 * nbt * 64 / ms / 1e9,
-                      "pct_of_hbm_roofline": nbytes / ms / 1e6 / (6528.4 * world) * 100}), flush=True)
+    for mode, (ms, chk) in results.items():
+        print(json.dumps({"workload": "BSR 3x3 SpMM x 64 cols, %d^3 nodes (BASELINE configs[4])" % n, "kernel": mode,
+                          "n_gpus": world, "blocks": nbt, "ms": ms, "algorithmic_gbs": nbytes / ms / 1e6,
+                          "tflops": 2 * 9 * nbt * 64 / ms / 1e9,
+                          "pct_of_hbm_roofline": nbytes / ms / 1e6 / (6528.4 * world) * 100, "checksum_rank0": chk}), flush=True)
 op.close()
 dist.destroy_process_group()
