@@ -231,3 +231,114 @@ def test_split_compact_gather_reassemble(g4s, oracle):
             torch.cuda.synchronize()
             err = np.abs(y.cpu().numpy() - want[c0:c1])
             assert np.all(err <= 1e-12 * scale[c0:c1] + 1e-300)
+
+
+# ---------------------------------------------------------------- BASELINE configs at full size, by properties ------
+def test_full_size_config3_rmat_properties(g4s):
+    """BASELINE configs[2]: R-MAT scale 24, edge factor 16 (16 777 216 vertices, 2^28 generated edges, duplicates summed).
+    Size-independent properties: structure invariants of CSR(graph&), A*1 = row sums (checked against a segmented sum by
+    torch), linearity, and agreement of two kernel shapes."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~20 GB of device memory")
+    scale = 24
+    A = g4s.CSR.rmat(scale, 16, seed=20240601)
+    n = 1 << scale
+    assert A.rows == n and A.cols == n and 0 < A.nnz <= 1 << 28
+    rp, ci, va = A.device_arrays()
+    from g4s_b200.dist import _DevArray
+
+    rowptr = torch.as_tensor(_DevArray(rp, n + 1, "<i4"), device="cuda")
+    colids = torch.as_tensor(_DevArray(ci, A.nnz, "<i4"), device="cuda")
+    values = torch.as_tensor(_DevArray(va, A.nnz, "<f8"), device="cuda")
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == A.nnz and bool((rowptr[1:] >= rowptr[:-1]).all())
+    assert int(colids.min()) >= 0 and int(colids.max()) < n
+    # strictly ascending columns inside every row (duplicates were summed): a drop is only allowed at a row start
+    drop = torch.nonzero(colids[1:] <= colids[:-1]).flatten() + 1
+    is_start = torch.zeros(A.nnz + 1, dtype=torch.bool, device="cuda")
+    is_start[rowptr.long()] = True
+    assert bool(is_start[drop].all())
+    del drop, is_start
+    ones = torch.ones(n, dtype=torch.float64, device="cuda")
+    y = torch.empty(n, dtype=torch.float64, device="cuda")
+    A.spmv_device(ones.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    want = torch.segment_reduce(values, "sum", offsets=rowptr.long())
+    assert float((y - want).abs().max()) <= 1e-12 * float(want.max())          # values are U(0,1): no cancellation
+    assert abs(float(y.sum()) - float(values.sum())) <= 1e-12 * float(values.sum())
+    g = torch.Generator(device="cuda").manual_seed(11)
+    u = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    v = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+    yu, yv, yw, y2 = (torch.empty_like(y) for _ in range(4))
+    A.spmv_device(u.data_ptr(), yu.data_ptr())
+    A.spmv_device(v.data_ptr(), yv.data_ptr())
+    w = 2.0 * u + 3.0 * v
+    A.spmv_device(w.data_ptr(), yw.data_ptr())
+    torch.cuda.synchronize()
+    bound = 2.0 * yu + 3.0 * yv                                               # = |A||w| for positive data
+    assert bool(((yw - bound).abs() <= 1e-12 * bound + 1e-300).all())
+    A.set_tuning(0, 6)                                                         # the long-row kernel shape on the same data
+    A.spmv_device(u.data_ptr(), y2.data_ptr())
+    torch.cuda.synchronize()
+    A.set_tuning(0, 0)
+    assert bool(((y2 - yu).abs() <= 1e-12 * yu + 1e-300).all())
+
+
+def test_dev_size_config5_bsr_closed_form(g4s):
+    """BASELINE configs[4] at its development size (128^3-node hex mesh, 27-block stencil, 3x3 blocks: diagonal 26 I + J,
+    off-diagonal -I - 0.1 J): with B = 1 every entry of block row (i,j,k) is 29 - 1.3 (#neighbours), and every
+    kernel / schedule must give the same C."""
+    import torch
+
+    from g4s_b200._lib import check
+    from g4s_b200.dist import _DevArray
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30e9:
+        pytest.skip("needs ~12 GB of device memory")
+    n, ncol = 128, 64
+    P = g4s.CSR.laplacian3d27(n)
+    rp, ci, va = P.device_arrays()
+    nb, mb = P.nnz, P.rows
+    vals = torch.as_tensor(_DevArray(va, nb, "<f8"), device="cuda")
+    J = torch.ones(3, 3, dtype=torch.float64, device="cuda")
+    I3 = torch.eye(3, dtype=torch.float64, device="cuda")
+    diag = (vals > 0).double()[:, None, None]
+    blocks = (diag * (26 * I3 + J) + (1 - diag) * (-I3 - 0.1 * J)).contiguous().reshape(-1)
+    del diag
+    B = torch.ones(mb * 3 * ncol, dtype=torch.float64, device="cuda")
+    c = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    c[0] = c[-1] = 2.0
+    neigh = (c[:, None, None] * c[None, :, None] * c[None, None, :]).reshape(-1) - 1.0
+    want = (29.0 - 1.3 * neigh)[:, None].expand(mb, 3 * ncol).reshape(-1)
+    L = g4s.lib()
+    outs = []
+    for variant in (1, 4, 2):
+        Cd = torch.full((mb * 3 * ncol,), -7.0, dtype=torch.float64, device="cuda")
+        check(L.g4s_bsr_spmm_set_variant(C.c_int(variant)))
+        check(L.g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci),
+                                    C.c_void_p(blocks.data_ptr()), C.c_int(ncol), C.c_void_p(B.data_ptr()),
+                                    C.c_void_p(Cd.data_ptr()), C.c_void_p(0)))
+        torch.cuda.synchronize()
+        L.g4s_bsr_spmm_set_variant(C.c_int(0))
+        assert float((Cd - want).abs().max()) <= 1e-12 * (29.0 + 1.3 * 26), variant
+        outs.append(Cd)
+    order = np.empty(mb, dtype=np.int32)
+    check(L.g4s_grid_pencil_order(C.c_int(n), C.c_int(n), C.c_int(n), C.c_int(4), C.c_int(4),
+                                  order.ctypes.data_as(C.c_void_p), None, None))
+    od = torch.from_numpy(order).cuda()
+    # random right-hand side: the ordered schedule is the K-packed kernel row by row, so C is bit-identical
+    g = torch.Generator(device="cuda").manual_seed(777)
+    B.copy_(torch.rand(mb * 3 * ncol, dtype=torch.float64, device="cuda", generator=g) * 2 - 1)
+    C1, C2 = torch.empty_like(B), torch.empty_like(B)
+    check(L.g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci),
+                                C.c_void_p(blocks.data_ptr()), C.c_int(ncol), C.c_void_p(B.data_ptr()),
+                                C.c_void_p(C1.data_ptr()), C.c_void_p(0)))
+    check(L.g4s_bsr3_spmm64_ordered_device(C.c_int(mb), C.c_int(mb), C.c_void_p(rp), C.c_void_p(ci),
+                                           C.c_void_p(blocks.data_ptr()), C.c_void_p(B.data_ptr()),
+                                           C.c_void_p(C2.data_ptr()), C.c_void_p(od.data_ptr()), C.c_void_p(0), C.c_int(0),
+                                           C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert torch.equal(C1, C2)
