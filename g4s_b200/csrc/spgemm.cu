@@ -16,6 +16,9 @@
 //   class 4  w <= 2048     one 256-thread CTA per row, 4096 slots
 //   class 5  w <= 8192     one 1024-thread CTA per row, 8192 slots
 //   class 6  larger        one CTA per row, power-of-two table in global memory (persistent CTAs own a slab)
+//   classes 4-6, products with at most 2^20 columns: DENSE ACCUMULATOR instead (spgemm_spa_kernel): one bit per column
+//                          in shared memory, one double per column in an L2-resident slab, sorted output by walking
+//                          the bitmap — no probing, no sort
 // Classes 1 and 2 keep the reference's sequential accumulation order: their VALUES are bit-identical to it.
 // Open addressing with linear probing, empty = -1, as the reference (hash_mult.h:89-101), with a multiplicative hash
 // on the high bits instead of (key * 107) & mask (see hash_slot).  Classes 3-6 insert with atomicCAS on the key and
@@ -678,6 +681,117 @@ __global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a,
     }
 }
 
+// class 6, dense accumulator (used when the product has at most SPA_MAX_COLS columns).  A row with tens of thousands of
+// distinct columns does not need a hash table at all: the CTA keeps ONE BIT per column in shared memory (the row's
+// pattern) and, in the numeric phase, one double per column in a global-memory slab that stays in L2 (red.add.f64, no
+// probing, no CAS).  Walking the bitmap in order then yields the row SORTED for free — the global-memory bitonic sort of
+// the hash version was most of its time (R-MAT A*A: 115 ms).  The slab is all zero between rows: emitting a column
+// resets its accumulator.  Rows are handed out through an atomic counter (their work differs by orders of magnitude);
+// rows of B longer than SPA_LONG_B are walked by the whole CTA instead of one lane group.
+constexpr int SPA_MAX_COLS = 1 << 20;   // 128 KB of bitmap
+constexpr int SPA_LONG_B = 2048;
+template <bool NUMERIC>
+__global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, const int *__restrict__ list, int nlist,
+                                                           double *__restrict__ slabs, int nwords,
+                                                           int *__restrict__ next_row) {
+    extern __shared__ unsigned spa_sm[];
+    unsigned *bm = spa_sm;                 // [nwords] one bit per column of C
+    int *wsum = reinterpret_cast<int *>(spa_sm + nwords);  // [32] per-warp counts, [32] = total, [33] = row index
+    constexpr unsigned FULL = 0xffffffffu;
+    double *dense = slabs + (size_t)blockIdx.x * a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int sub_lg = a.sub_lg;
+    const int SUB = 1 << sub_lg, nsub = blockDim.x >> sub_lg, my_sub = threadIdx.x >> sub_lg, sl = threadIdx.x & (SUB - 1);
+    // words of the bitmap owned by this warp: a contiguous span, a multiple of 32 long
+    const int span = ((nwords + nwarps - 1) / nwarps + 31) & ~31;
+    const int w0 = warp * span;
+    for (int w = threadIdx.x; w < nwords; w += blockDim.x) bm[w] = 0u;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) wsum[33] = atomicAdd(next_row, 1);
+        __syncthreads();
+        const int idx = wsum[33];
+        if (idx >= nlist) break;
+        const int row = list ? list[idx] : idx;
+        const int as = a.arpt[row], ae = a.arpt[row + 1];
+        // short rows of B: one lane group each
+        for (int j = as + my_sub; j < ae; j += nsub) {
+            const int k = a.acol[j];
+            const int bs = a.brpt[k], be = a.brpt[k + 1];
+            if (be - bs >= SPA_LONG_B) continue;
+            const double av = NUMERIC ? a.aval[j] : 0.0;
+            for (int p = bs + sl; p < be; p += SUB) {
+                const int col = __ldg(a.bcol + p);
+                atomicOr(&bm[col >> 5], 1u << (col & 31));
+                if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+            }
+        }
+        // long rows of B: the whole CTA
+        for (int j = as; j < ae; ++j) {
+            const int k = a.acol[j];
+            const int bs = a.brpt[k], be = a.brpt[k + 1];
+            if (be - bs < SPA_LONG_B) continue;
+            const double av = NUMERIC ? a.aval[j] : 0.0;
+            for (int p = bs + threadIdx.x; p < be; p += blockDim.x) {
+                const int col = __ldg(a.bcol + p);
+                atomicOr(&bm[col >> 5], 1u << (col & 31));
+                if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+            }
+        }
+        if (NUMERIC) __threadfence();  // the accumulators are read back by other threads below
+        __syncthreads();
+        // count the bits of this warp's span, scan the warp totals
+        int c = 0;
+        for (int w = w0 + lane; w < min(w0 + span, nwords); w += 32) c += __popc(bm[w]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (lane == 0) wsum[warp] = c;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = lane < nwarps ? wsum[lane] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += up;
+            }
+            wsum[lane] = inc - v;  // exclusive
+            if (lane == 31) wsum[32] = inc;
+        }
+        __syncthreads();
+        if (!NUMERIC) {
+            if (threadIdx.x == 0) a.row_nnz[row] = wsum[32];
+            for (int w = w0 + lane; w < min(w0 + span, nwords); w += 32) bm[w] = 0u;
+            continue;
+        }
+        // emit the columns in ascending order; every emitted accumulator goes back to zero
+        int running = a.crpt[row] + wsum[warp];
+        for (int wb = w0; wb < min(w0 + span, nwords); wb += 32) {  // warp-uniform trip count
+            const int w = wb + lane;
+            unsigned bits = w < nwords ? bm[w] : 0u;
+            if (w < nwords) bm[w] = 0u;
+            const int cnt = __popc(bits);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += up;
+            }
+            int pos = running + inc - cnt;
+            running += __shfl_sync(FULL, inc, 31);
+            while (bits) {
+                const int col = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                a.ccol[pos] = col;
+                a.cval[pos] = __ldcg(dense + col);
+                dense[col] = 0.0;
+                ++pos;
+            }
+        }
+        __threadfence();  // the zeros must be in place before the next row's red.add
+    }
+}
+
 static thread_local double t_phase_ms[4] = {0, 0, 0, 0};
 
 template <int GROUP, int TABLE, int WMAX, int THREADS, bool NUMERIC>
@@ -731,6 +845,10 @@ struct Bins {
     int merge_lists = MERGE_MAX_A;  // longest row of A in class 1
 };
 
+static bool use_spa(int cols);
+static int spa_from();
+static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream);
+
 static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab_keys, double *slab_vals,
                      long long slab_slots, int slab_ctas, cudaStream_t stream) {
     int rc;
@@ -745,16 +863,22 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
         G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
     }
     if ((rc = launch_thread_row<32, 128>(a, list(2), b.count[2], numeric, stream))) return rc;
+    // classes spa_from()..6 go through the dense accumulator when the product is narrow enough for the bitmap
+    const int first_spa = use_spa(a.N) ? spa_from() : NCLASS;
     if (numeric) {  // tables sized by nnz (load factor <= 1/2 up to the class bound), values + compaction buffers
-        if ((rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream))) return rc;
-        if ((rc = launch_smem<256, 4096, 2048, 256, true>(a, list(4), b.count[4], stream))) return rc;
-        if ((rc = launch_smem<1024, 8192, 8192, 1024, true>(a, list(5), b.count[5], stream))) return rc;
+        if (first_spa > 3 && (rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream))) return rc;
+        if (first_spa > 4 && (rc = launch_smem<256, 4096, 2048, 256, true>(a, list(4), b.count[4], stream))) return rc;
+        if (first_spa > 5 && (rc = launch_smem<1024, 8192, 8192, 1024, true>(a, list(5), b.count[5], stream))) return rc;
     } else {        // keys only, sized by min(work, cols)
-        if ((rc = launch_smem<32, 1024, 1, 256, false>(a, list(3), b.count[3], stream))) return rc;
-        if ((rc = launch_smem<256, 4096, 1, 256, false>(a, list(4), b.count[4], stream))) return rc;
-        if ((rc = launch_smem<1024, 16384, 1, 1024, false>(a, list(5), b.count[5], stream))) return rc;
+        if (first_spa > 3 && (rc = launch_smem<32, 1024, 1, 256, false>(a, list(3), b.count[3], stream))) return rc;
+        if (first_spa > 4 && (rc = launch_smem<256, 4096, 1, 256, false>(a, list(4), b.count[4], stream))) return rc;
+        if (first_spa > 5 && (rc = launch_smem<1024, 16384, 1, 1024, false>(a, list(5), b.count[5], stream))) return rc;
     }
-    if (b.count[6]) {
+    for (int c = std::max(first_spa, 3); c < 6; ++c)
+        if (b.count[c] && (rc = launch_spa(a, list(c), b.count[c], numeric, stream))) return rc;
+    if (b.count[6] && use_spa(a.N)) {
+        if ((rc = launch_spa(a, list(6), b.count[6], numeric, stream))) return rc;
+    } else if (b.count[6]) {
         if (numeric)
             spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
                                                                       slab_keys, slab_vals, slab_slots);
@@ -777,6 +901,9 @@ struct Workspace {
     unsigned long long *dtotal = nullptr;
     int *hcount = nullptr;  // pinned
     unsigned long long *htotal = nullptr;
+    double *spa_dense = nullptr;  // dense accumulators of the class-6 SPA kernel: all zero between launches
+    size_t spa_doubles = 0;
+    int *spa_next = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int ensure(int M) {
         int dev = 0;
@@ -788,6 +915,7 @@ struct Workspace {
         if (!dcount) {
             G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (4 * NCLASS + 2)));
             G4S_CUDA(cudaMalloc(&dtotal, sizeof(unsigned long long)));
+            G4S_CUDA(cudaMalloc(&spa_next, sizeof(int)));
             G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 2)));
             G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
             for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
@@ -809,8 +937,55 @@ struct Workspace {
         }
         return G4S_OK;
     }
+    int ensure_spa(size_t doubles, cudaStream_t stream) {
+        if (doubles <= spa_doubles) return G4S_OK;
+        if (spa_dense) cudaFree(spa_dense);
+        spa_dense = nullptr;
+        spa_doubles = 0;
+        G4S_CUDA(cudaMalloc(&spa_dense, sizeof(double) * doubles));
+        G4S_CUDA(cudaMemsetAsync(spa_dense, 0, sizeof(double) * doubles, stream));
+        spa_doubles = doubles;
+        return G4S_OK;
+    }
 };
 static thread_local Workspace t_ws;
+
+// class 6 through the dense accumulator?  (G4S_SPGEMM_SPA=0 keeps the global hash tables)
+static bool use_spa(int cols) {
+    const char *e = getenv("G4S_SPGEMM_SPA");  // read per call: the tests switch between the two class-6 kernels
+    return (!e || atoi(e) != 0) && cols <= SPA_MAX_COLS;
+}
+// first size class routed to the dense accumulator (G4S_SPGEMM_SPA_FROM = 3..6)
+static int spa_from() {
+    const char *e = getenv("G4S_SPGEMM_SPA_FROM");
+    const int v = e ? atoi(e) : 4;  // measured: R-MAT A*A 56 ms (6) / 16.2 (5) / 14.6 (4); class 3 (short rows) is faster hashed
+    return v < 3 ? 3 : (v > 6 ? 6 : v);
+}
+static int spa_grid(int cols, int rows_in_class) {
+    const size_t smem = sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    return std::max(1, std::min(rows_in_class, sm_count() * per_sm));
+}
+static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
+    Workspace &ws = t_ws;
+    const int nwords = (a.N + 31) / 32;
+    const size_t smem = sizeof(unsigned) * ((size_t)nwords + 34);
+    static bool configured = false;
+    if (!configured) {
+        const int cap = (int)(sizeof(unsigned) * (SPA_MAX_COLS / 32 + 34));
+        G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        configured = true;
+    }
+    const int grid = spa_grid(a.N, nlist);
+    int rc = ws.ensure_spa((size_t)grid * a.N, stream);
+    if (rc) return rc;
+    G4S_CUDA(cudaMemsetAsync(ws.spa_next, 0, sizeof(int), stream));
+    if (numeric) spgemm_spa_kernel<true><<<grid, 1024, smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
+    else spgemm_spa_kernel<false><<<grid, 1024, smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
+    G4S_CHECK_LAUNCH("spgemm_spa_kernel");
+    return G4S_OK;
+}
 
 int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     if (A->cols != B->rows) return fail(G4S_ERR_SHAPE, "g4s_spgemm: A.cols != B.rows");
@@ -884,7 +1059,7 @@ int spgemm_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) {
     long long slab_slots = 0;
     int slab_ctas = 0;
     auto ensure_slabs = [&](int rows_in_class) -> int {
-        if (!rows_in_class || slab_keys) return G4S_OK;
+        if (!rows_in_class || slab_keys || use_spa(N)) return G4S_OK;
         const long long w = std::min<long long>(b.max_work, N);
         slab_slots = 16384;
         while (slab_slots < 2 * w) slab_slots <<= 1;

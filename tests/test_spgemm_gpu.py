@@ -73,14 +73,24 @@ CASES = {
     "rand_dense_rows": lambda: (random_csr(64, 64, 0.6, 4), random_csr(64, 64, 0.6, 5)),  # w capped by cols
     "banded_20": lambda: (banded(600, 20, 6),) * 2,                                    # work 1681: class 3
     "banded_35": lambda: (banded(5000, 35, 7),) * 2,                                   # work 5041, cols 5000: class 4
-    "powerlaw_hub": lambda: (powerlaw_csr(12000, 7, max_deg=6000),) * 2,               # class 5 (global tables)
+    "powerlaw_hub": lambda: (powerlaw_csr(12000, 7, max_deg=6000),) * 2,               # class 5
+    "powerlaw_big_hub": lambda: (powerlaw_csr(24000, 9, max_deg=2500),) * 2,           # class 6 (dense accumulator; long B rows)
 }
+
+
+_ORACLE_CACHE = {}
+
+
+def case_with_oracle(oracle, name):
+    if name not in _ORACLE_CACHE:
+        A, B = CASES[name]()
+        _ORACLE_CACHE[name] = (A, B) + tuple(oracle_product(oracle, A, B))
+    return _ORACLE_CACHE[name]
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_spgemm_matches_oracle(g4s, oracle, name):
-    A, B = CASES[name]()
-    rpt, col, val, scale = oracle_product(oracle, A, B)
+    A, B, rpt, col, val, scale = case_with_oracle(oracle, name)
     Ad, Bd = as_csr(g4s, A), as_csr(g4s, B)
     C = g4s.HashSpGEMM(Ad, Bd).to_host()
     assert (C.rows, C.cols) == (A[0], B[1])
@@ -94,6 +104,14 @@ def test_spgemm_matches_oracle(g4s, oracle, name):
     assert t.total > 0 and abs(t.create + t.spmm + t.export_csr + t.destroy - t.total) < 1e-3
     # reference-style comparison (CSR::operator==, EPSILON 1e-3)
     assert C == g4s.CSR(A[0], B[1], rpt, col, val)
+
+
+def test_class6_global_hash_tables_still_match(g4s, oracle, monkeypatch):
+    """Class 6 has two kernels: the dense accumulator (products with at most 2^20 columns) and hash tables in global
+    memory (anything wider).  The wide case is too big for a parity test, so the hash kernel is forced on a small one."""
+    monkeypatch.setenv("G4S_SPGEMM_SPA", "0")
+    A, B, rpt, col, val, scale = case_with_oracle(oracle, "powerlaw_big_hub")
+    check_against(g4s.HashSpGEMM(as_csr(g4s, A), as_csr(g4s, B)).to_host(), rpt, col, val, scale)
 
 
 def test_tiny_row_classes_are_bit_exact(g4s, oracle):
