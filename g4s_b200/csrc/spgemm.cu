@@ -962,135 +962,11 @@ static int spa_from() {
     return v < 3 ? 3 : (v > 6 ? 6 : v);
 }
 // CTAs of the dense-accumulator kernel: two per SM when the bitmap allows.  Capping the grid so that all fp64 slabs fit
-// L2 (96 MB) was measured and is worse: R-MAT 18 100 -> 305 ms — the parallelism is worth more than the spill to DRAM.
+// L2 (96 MB) was measured and is worse (R-MAT 18: 100 -> 305 ms): the parallelism is worth more than the spill to DRAM.
 static int spa_grid(int cols, int rows_in_class) {
     const size_t smem = sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34);
     const int per_sm = smem <= 100 * 1024 ? 2 : 1;
     return std::max(1, std::min(rows_in_class, sm_count() * per_sm));
-}
-static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream);
-
-static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab_keys, double *slab_vals,
-                     long long slab_slots, int slab_ctas, cudaStream_t stream) {
-    int rc;
-    auto list = [&](int c) -> const int * { return b.identity ? nullptr : b.perm + b.offset[c]; };
-    if (b.count[1]) {
-        const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
-        const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
-        if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
-        else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
-        else if (k5) spgemm_merge_row_kernel<5, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
-        else spgemm_merge_row_kernel<MERGE_MAX_A, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
-        G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
-    }
-    if ((rc = launch_thread_row<32, 128>(a, list(2), b.count[2], numeric, stream))) return rc;
-    // classes spa_from()..6 go through the dense accumulator when the product is narrow enough for the bitmap
-    const int first_spa = use_spa(a.N) ? spa_from() : NCLASS;
-    if (numeric) {  // tables sized by nnz (load factor <= 1/2 up to the class bound), values + compaction buffers
-        if (first_spa > 3 && (rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream))) return rc;
-        if (first_spa > 4 && (rc = launch_smem<256, 4096, 2048, 256, true>(a, list(4), b.count[4], stream))) return rc;
-        if (first_spa > 5 && (rc = launch_smem<1024, 8192, 8192, 1024, true>(a, list(5), b.count[5], stream))) return rc;
-    } else {        // keys only, sized by min(work, cols)
-        if (first_spa > 3 && (rc = launch_smem<32, 1024, 1, 256, false>(a, list(3), b.count[3], stream))) return rc;
-        if (first_spa > 4 && (rc = launch_smem<256, 4096, 1, 256, false>(a, list(4), b.count[4], stream))) return rc;
-        if (first_spa > 5 && (rc = launch_smem<1024, 16384, 1, 1024, false>(a, list(5), b.count[5], stream))) return rc;
-    }
-    for (int c = std::max(first_spa, 3); c < 6; ++c)
-        if (b.count[c] && (rc = launch_spa(a, list(c), b.count[c], numeric, stream))) return rc;
-    if (b.count[6] && use_spa(a.N)) {
-        if ((rc = launch_spa(a, list(6), b.count[6], numeric, stream))) return rc;
-    } else if (b.count[6]) {
-        if (numeric)
-            spgemm_global_kernel<true><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
-                                                                      slab_keys, slab_vals, slab_slots);
-        else
-            spgemm_global_kernel<false><<<slab_ctas, 1024, 0, stream>>>(a, list(6), b.count[6], b.row_work,
-                                                                       slab_keys, slab_vals, slab_slots);
-        G4S_CHECK_LAUNCH("spgemm_global_kernel");
-    }
-    return G4S_OK;
-}
-
-// Scratch reused across calls on the calling thread (row work, row lists, counters): SpGEMM is called in loops
-// (the reference's driver runs it 11 times, mm/src/mkl_spgemm.cpp:67-79) and cudaMalloc is a device-wide sync.
-struct Workspace {
-    int device = -1;
-    size_t rows_cap = 0;
-    int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
-    unsigned char *row_class = nullptr, *num_class = nullptr;
-    int *perm2 = nullptr;
-    unsigned long long *dtotal = nullptr;
-    int *hcount = nullptr;  // pinned
-    unsigned long long *htotal = nullptr;
-    double *spa_dense = nullptr;  // dense accumulators of the class-6 SPA kernel: all zero between launches
-    size_t spa_doubles = 0;
-    int *spa_next = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int ensure(int M) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev != device) {  // one workspace per thread; a device switch starts over
-            *this = Workspace();
-            device = dev;
-        }
-        if (!dcount) {
-            G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (4 * NCLASS + 2)));
-            G4S_CUDA(cudaMalloc(&dtotal, sizeof(unsigned long long)));
-            G4S_CUDA(cudaMalloc(&spa_next, sizeof(int)));
-            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 2)));
-            G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
-            for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
-        }
-        if ((size_t)M + 1 > rows_cap) {
-            if (row_work) cudaFree(row_work);
-            if (perm) cudaFree(perm);
-            if (row_nnz) cudaFree(row_nnz);
-            if (row_class) cudaFree(row_class);
-            if (num_class) cudaFree(num_class);
-            if (perm2) cudaFree(perm2);
-            rows_cap = (size_t)M + 1;
-            G4S_CUDA(cudaMalloc(&row_work, sizeof(int) * rows_cap));
-            G4S_CUDA(cudaMalloc(&perm, sizeof(int) * rows_cap));
-            G4S_CUDA(cudaMalloc(&row_nnz, sizeof(int) * rows_cap));
-            G4S_CUDA(cudaMalloc(&row_class, rows_cap));
-            G4S_CUDA(cudaMalloc(&num_class, rows_cap));
-            G4S_CUDA(cudaMalloc(&perm2, sizeof(int) * rows_cap));
-        }
-        return G4S_OK;
-    }
-    int ensure_spa(size_t doubles, cudaStream_t stream) {
-        if (doubles <= spa_doubles) return G4S_OK;
-        if (spa_dense) cudaFree(spa_dense);
-        spa_dense = nullptr;
-        spa_doubles = 0;
-        G4S_CUDA(cudaMalloc(&spa_dense, sizeof(double) * doubles));
-        G4S_CUDA(cudaMemsetAsync(spa_dense, 0, sizeof(double) * doubles, stream));
-        spa_doubles = doubles;
-        return G4S_OK;
-    }
-};
-static thread_local Workspace t_ws;
-
-// class 6 through the dense accumulator?  (G4S_SPGEMM_SPA=0 keeps the global hash tables)
-static bool use_spa(int cols) {
-    const char *e = getenv("G4S_SPGEMM_SPA");  // read per call: the tests switch between the two class-6 kernels
-    return (!e || atoi(e) != 0) && cols <= SPA_MAX_COLS;
-}
-// first size class routed to the dense accumulator (G4S_SPGEMM_SPA_FROM = 3..6)
-static int spa_from() {
-    const char *e = getenv("G4S_SPGEMM_SPA_FROM");
-    const int v = e ? atoi(e) : 4;  // measured: R-MAT A*A 56 ms (6) / 16.2 (5) / 14.6 (4); class 3 (short rows) is faster hashed
-    return v < 3 ? 3 : (v > 6 ? 6 : v);
-}
-// CTAs of the dense-accumulator kernel: at most two per SM (1024 threads each), and no more than keep their fp64 slabs
-// (8 bytes per column each) inside `budget` MB of L2 — beyond that the red.add traffic spills to DRAM
-static int spa_grid(int cols, int rows_in_class) {
-    const size_t smem = sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34);
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
-    const char *e = getenv("G4S_SPA_L2MB");
-    const long long budget = (e ? atoll(e) : 96) << 20;
-    const long long fit = std::max<long long>(sm_count() / 4, budget / (8LL * std::max(cols, 1)));
-    return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(rows_in_class, (long long)sm_count() * per_sm), fit));
 }
 static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
     Workspace &ws = t_ws;
