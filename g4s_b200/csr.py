@@ -270,6 +270,14 @@ def HashSpGEMM(a, b, stream=None):
     return CSR._from_handle(h)
 
 
+def OuterSpGEMM(a, b, stream=None):
+    """OuterSpGEMM (mm/inc/outer_mult.h:271-542), the expand - sort - compress "join": same C as HashSpGEMM, values summed
+    in the reference's sequential order for every row."""
+    h = C.c_void_p()
+    check(lib().g4s_spgemm_esc_device(a.handle, b.handle, C.byref(h), _stream_ptr(stream)))
+    return CSR._from_handle(h)
+
+
 def mkl(A, B, timing=None):
     """mkl(A, B, C, timing) (mm/inc/mkl_mult.h:113-117 -> :40-110): host CSR in, host CSR out, phases in timing."""
     a, b = A.to_host(), B.to_host()

@@ -142,6 +142,12 @@ int g4s_spgemm_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
 /* Per-phase device milliseconds of the last g4s_spgemm_device on this thread: binning, symbolic, scan+alloc,
  * numeric(+sort). */
 int g4s_spgemm_last_phase_ms(double *ms4);
+/* The same product by expand - sort - compress, the GPU form of the reference's OuterSpGEMM "join"
+ * (mm/inc/outer_mult.h:271-542: (row, col, value) triples, radix sort on (row << 32) | col, equal keys summed).  Same CSR
+ * as g4s_spgemm_device; the values are summed in the reference's sequential order for EVERY row (bit-identical to
+ * HashSpGEMM<false,true>).  Slower and 32 bytes of scratch per intermediate product (at most 2^31-1 of them): the
+ * library's second, independent SpGEMM, for cross-checks and for the reference's algorithm inventory. */
+int g4s_spgemm_esc_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
 
 /* compute_flop / get_flop (mm/inc/mkl_mult.h:8-38, hash_mult.h:45-62): intermediate products, 64-bit.
  * row_work_dev may be NULL; else int32[rows] on the device (BIN::set_intprod_num, BIN.h:77-95). */

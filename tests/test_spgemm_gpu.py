@@ -106,6 +106,18 @@ def test_spgemm_matches_oracle(g4s, oracle, name):
     assert C == g4s.CSR(A[0], B[1], rpt, col, val)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_outer_spgemm_is_bit_exact(g4s, oracle, name):
+    """The expand - sort - compress path (OuterSpGEMM, mm/inc/outer_mult.h:271-542) sums every output entry in the
+    reference's sequential order: pattern AND values equal HashSpGEMM<false,true>'s bit for bit, for every row class."""
+    A, B, rpt, col, val, _ = case_with_oracle(oracle, name)
+    C = g4s.OuterSpGEMM(as_csr(g4s, A), as_csr(g4s, B)).to_host()
+    assert (C.rows, C.cols) == (A[0], B[1])
+    np.testing.assert_array_equal(C.rowptr, rpt)
+    np.testing.assert_array_equal(C.colids, col)
+    np.testing.assert_array_equal(C.values, val)
+
+
 def test_class6_global_hash_tables_still_match(g4s, oracle, monkeypatch):
     """Class 6 has two kernels: the dense accumulator (products with at most 2^20 columns) and hash tables in global
     memory (anything wider).  The wide case is too big for a parity test, so the hash kernel is forced on a small one."""
@@ -178,3 +190,8 @@ def test_full_size_config4_properties(g4s):
     assert sorted(val[s:e].tolist()) == sorted([20.0] + [-8.0] * 4 + [2.0] * 4 + [1.0] * 4)
     assert col[s:e].tolist() == [r - 2 * n, r - n - 1, r - n, r - n + 1, r - 2, r - 1, r, r + 1, r + 2,
                                  r + n - 1, r + n, r + n + 1, r + 2 * n]
+    # the library's second SpGEMM (expand - sort - compress) gives the identical CSR, bit for bit (the merge class keeps
+    # the reference's accumulation order, and so does the join)
+    Eh = g4s.OuterSpGEMM(A, A).to_host()
+    assert np.array_equal(Eh.rowptr, Ch.rowptr) and np.array_equal(Eh.colids, Ch.colids)
+    assert np.array_equal(Eh.values, Ch.values)

@@ -28,6 +28,8 @@ def run(name, A, reps=3):
           % (name, A.rows, A.nnz, flop / 2, nnzc, ms, flop / ms / 1e6, ph[0], ph[1], ph[2], ph[3]), flush=True)
 
 
+if os.environ.get("SPGEMM_ESC"):  # time the expand - sort - compress path instead
+    g4s_b200.HashSpGEMM = g4s_b200.OuterSpGEMM
 which = sys.argv[1:] or ["lap3d64", "lap3d100", "rmat16", "rmat18", "lap2d2048"]
 for w in which:
     if w.startswith("lap3d"):
