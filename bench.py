@@ -342,9 +342,85 @@ def run_ours(args, rank, world):
             except Exception:
                 ref = None
             line["spgemm"]["cpu_baseline"] = cpu_spgemm(ref, oracle, SPGEMM_GRID)
+        if not args.no_other:
+            try:
+                line["other_configs"] = bench_other_configs(g4s_b200, torch, peak)
+            except Exception as e:  # the headline line must not depend on the riders
+                line["other_configs"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_other_configs(g4s_b200, torch, peak):
+    """The remaining BASELINE configs on one GPU, device-timed (CUDA events, 3 warm-ups, 20 / 5 launches): configs[0]
+    (2-D 5-point SpMV, L2-resident), configs[2] (R-MAT scale 24 SpMV) and configs[4] at its development size (BSR 3x3 SpMM x 64
+    columns on a 128^3-node mesh; 256^3 is the 8-GPU size).  `frac` = algorithmic bytes / time over the measured HBM peak."""
+    import ctypes as C
+
+    import numpy as np
+
+    from g4s_b200._lib import check
+    from g4s_b200.dist import _DevArray
+
+    L = g4s_b200.lib()
+
+    def timeit(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    for key, make, note in (
+            ("configs[0] spmv 2-D 5-point n=1000", lambda: g4s_b200.CSR.laplacian2d(1000), "80 MB: L2-resident"),
+            ("configs[2] spmv R-MAT scale 24 ef 16", lambda: g4s_b200.CSR.rmat(24, 16, seed=20240601), "duplicates summed")):
+        A = make()
+        nbytes, flops = A.spmv_cost()
+        x = torch.rand(A.cols, dtype=torch.float64, device="cuda") - 0.5
+        y = torch.empty(A.rows, dtype=torch.float64, device="cuda")
+        ms = timeit(lambda: A.spmv_device(x.data_ptr(), y.data_ptr()), 20)
+        out[key] = {"rows": A.rows, "nnz": A.nnz, "ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "gflops": flops / ms / 1e6,
+                    "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "note": note}
+        A.make_empty()
+        del x, y
+    n, ncol = 128, 64
+    P = g4s_b200.CSR.laplacian3d27(n)
+    rp, ci, va = P.device_arrays()
+    nb, mb = P.nnz, P.rows
+    vals = torch.as_tensor(_DevArray(va, nb, "<f8"), device="cuda")
+    J = torch.ones(3, 3, dtype=torch.float64, device="cuda")
+    I3 = torch.eye(3, dtype=torch.float64, device="cuda")
+    diag = (vals > 0).double()[:, None, None]
+    blocks = (diag * (26 * I3 + J) + (1 - diag) * (-I3 - 0.1 * J)).contiguous().reshape(-1)
+    del diag
+    g = torch.Generator(device="cuda").manual_seed(777)
+    B = torch.rand(mb * 3 * ncol, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    Cd = torch.empty(mb * 3 * ncol, dtype=torch.float64, device="cuda")
+    order = np.empty(mb, dtype=np.int32)
+    check(L.g4s_grid_pencil_order(C.c_int(n), C.c_int(n), C.c_int(n), C.c_int(4), C.c_int(4),
+                                  order.ctypes.data_as(C.c_void_p), None, None))
+    od = torch.from_numpy(order).cuda()
+    nbytes = 76.0 * nb + 4 * (mb + 1) + 2 * 8.0 * 3 * mb * ncol
+    flops = 2.0 * 9 * nb * ncol
+    plain = timeit(lambda: check(L.g4s_bsr_spmm_device(
+        C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci), C.c_void_p(blocks.data_ptr()), C.c_int(ncol),
+        C.c_void_p(B.data_ptr()), C.c_void_p(Cd.data_ptr()), C.c_void_p(0))), 5)
+    tiled = timeit(lambda: check(L.g4s_bsr3_spmm64_ordered_device(
+        C.c_int(mb), C.c_int(mb), C.c_void_p(rp), C.c_void_p(ci), C.c_void_p(blocks.data_ptr()), C.c_void_p(B.data_ptr()),
+        C.c_void_p(Cd.data_ptr()), C.c_void_p(od.data_ptr()), C.c_void_p(0), C.c_int(0), C.c_void_p(0))), 5)
+    for name, ms in (("natural row order", plain), ("tile-major (4x4 pencil) row order", tiled)):
+        out["configs[4] bsr 3x3 spmm x 64 cols, 128^3 nodes, " + name] = {
+            "blocks": nb, "ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "tflops": flops / ms / 1e9,
+            "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+    P.make_empty()
+    return out
 
 
 def bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world):
@@ -442,6 +518,7 @@ def main():
                     help="multi-GPU x assembly (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-spgemm", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the single-GPU riders for configs[0], [2], [4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
