@@ -19,6 +19,16 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner when the box sets
+# NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the whole run and the line is written to the
+# original stdout by emit().
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -151,7 +161,7 @@ def run_reference(args, rank):
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -347,7 +357,7 @@ def run_ours(args, rank, world):
                 line["other_configs"] = bench_other_configs(g4s_b200, torch, peak)
             except Exception as e:  # the headline line must not depend on the riders
                 line["other_configs"] = {"error": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
