@@ -1,0 +1,23 @@
+"""The bench.py contract that can be checked without a GPU: the reference arm (the CPU baseline of the hot path) prints
+exactly ONE line on stdout, a JSON object with the keys the driver reads, whatever libraries write to stdout."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "spmv_achieved_gbs" and d["unit"] == "GB/s"
+    assert d["steps"] == 2 and d["n_gpus"] == 1 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("SpMV y=Ax, 3-D 27-point Laplacian n=400")
