@@ -9,6 +9,7 @@
 //   i64   rows, cols, nnz;  u64 checksum (of the three arrays, in file order);  u64 reserved
 //   i32 rowptr[rows+1];  i32 colids[nnz];  f64 values[nnz]
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -90,8 +91,9 @@ int g4s_csr_write_binary(const char *path, int rows, int cols, int nnz, const in
     if (!path || rows < 0 || cols < 0 || nnz < 0 || !rowptr || (nnz && (!colids || !values)))
         return fail(G4S_ERR_INVALID, "g4s_csr_write_binary: bad arguments");
     if (rowptr[0] != 0 || rowptr[rows] != nnz) return fail(G4S_ERR_INVALID, "g4s_csr_write_binary: rowptr does not span [0, nnz]");
-    // write to a temporary name and rename: a reader never sees a half-written cache
-    const std::string tmp = std::string(path) + ".tmp";
+    // write to a temporary name (per process: the ranks of a multi-GPU job may all miss the cache at once) and rename:
+    // a reader never sees a half-written cache
+    const std::string tmp = std::string(path) + ".tmp." + std::to_string((long long)getpid());
     FILE *f = fopen(tmp.c_str(), "wb");
     if (!f) return fail(G4S_ERR_IO, "unable to open file \"" + tmp + "\" for writing");
     Header h;

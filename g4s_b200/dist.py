@@ -363,12 +363,12 @@ class DistSpGEMM:
         """Returns (C_local, global_nnz_offset): this rank's rows of C and where they start in the global CSR."""
         C_local = HashSpGEMM(self.A_local, self.B)
         dev = torch.device("cuda", torch.cuda.current_device())
-        mine = torch.tensor([C_local.nnz], dtype=torch.int64, device=dev)
+        mine = torch.full((1,), C_local.nnz, dtype=torch.int64, device=dev)  # a fill kernel: no pageable copy, no sync
         every = torch.empty(self.world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(every, mine, group=self.group)
-        offset = int(every[:self.rank].sum().item())
-        self.global_nnz = int(every.sum().item())
-        return C_local, offset
+        counts = every.tolist()                                              # the step's one host read
+        self.global_nnz = int(sum(counts))
+        return C_local, int(sum(counts[:self.rank]))
 
 
 # ------------------------------------------------------------------------------------------------ BSR SpMM
