@@ -1,0 +1,104 @@
+"""Property tests (hypothesis) of the host-side pieces of the path: the row partitioner against the oracle's restatement of
+BIN::set_rows_offset (mm/inc/BIN.h:100-122), the binary CSR cache, the sub-matrix constructor, the CitcomS node-format
+converter on arbitrary small meshes, and the tile-major order helper."""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import g4s_b200
+
+L = g4s_b200.lib()
+FAST = settings(max_examples=40, deadline=None)
+
+
+@st.composite
+def csr_matrices(draw, max_rows=40, max_cols=40):
+    rows = draw(st.integers(1, max_rows))
+    cols = draw(st.integers(1, max_cols))
+    density = draw(st.floats(0.0, 0.5))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    m = sp.random(rows, cols, density=density, random_state=rng, format="csr", data_rvs=lambda n: rng.uniform(-1, 1, n))
+    m.sort_indices()
+    return g4s_b200.CSR(rows, cols, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.astype(np.float64))
+
+
+@FAST
+@given(st.lists(st.integers(0, 50), min_size=1, max_size=200), st.integers(1, 9))
+def test_partition_rows_cuts_are_monotone_cover_and_balanced(work, parts):
+    prefix = np.zeros(len(work) + 1, dtype=np.int64)
+    np.cumsum(work, out=prefix[1:])
+    cuts = np.zeros(parts + 1, dtype=np.int32)
+    assert L.g4s_partition_rows_i64(prefix.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_int(len(work)), C.c_int(parts),
+                                    cuts.ctypes.data_as(C.POINTER(C.c_int))) == 0
+    assert cuts[0] == 0 and cuts[-1] == len(work) and np.all(np.diff(cuts) >= 0)
+    # the rule of BIN::set_rows_offset: part p ends at the first row whose prefix reaches (p+1) * ceil(total / parts)
+    avg = -(-int(prefix[-1]) // parts)
+    for p in range(parts - 1):
+        want = min(int(np.searchsorted(prefix, avg * (p + 1), side="left")), len(work))
+        assert cuts[p + 1] == want
+        if 0 < cuts[p + 1] < len(work):  # no part carries more than the average plus one row's work
+            assert prefix[cuts[p + 1]] - prefix[cuts[p]] <= avg + max(work)
+
+
+@FAST
+@given(csr_matrices())
+def test_binary_cache_round_trip(tmp_path_factory, A):
+    path = tmp_path_factory.mktemp("cache") / "m.g4scsr"
+    A.save_binary(path)
+    B = g4s_b200.CSR.load_binary(path)
+    assert (B.rows, B.cols) == (A.rows, A.cols)
+    assert np.array_equal(B.rowptr, A.rowptr) and np.array_equal(B.colids, A.colids)
+    assert np.array_equal(B.values.view(np.int64), A.values.view(np.int64))
+
+
+@FAST
+@given(csr_matrices(), st.data())
+def test_submatrix_is_the_leading_block(A, data):
+    m = data.draw(st.integers(1, A.rows))
+    n = data.draw(st.integers(1, A.cols))
+    S = A.submatrix(m, n)
+    dense = sp.csr_matrix((A.values, A.colids, A.rowptr), shape=(A.rows, A.cols)).toarray()[:m, :n]
+    got = sp.csr_matrix((S.values, S.colids, S.rowptr), shape=(m, n)).toarray()
+    assert (S.rows, S.cols) == (m, n) and np.array_equal(got, dense)
+
+
+@settings(max_examples=15, deadline=None)
+@given(st.integers(2, 5), st.integers(2, 5), st.integers(2, 5), st.integers(0, 10 ** 6))
+def test_citcoms_converter_on_arbitrary_meshes(oracle, nox, noy, noz, seed):
+    rng = np.random.default_rng(seed)
+    nel = (nox - 1) * (noy - 1) * (noz - 1)
+    half = rng.uniform(-1, 1, (nel, 24, 24))
+    _, node_map, k1, k2, k3 = oracle.citcoms_mesh(nox, noy, noz, half + half.transpose(0, 2, 1))
+    nno = nox * noy * noz
+    rp, ci, blocks = g4s_b200.bsr_from_citcoms_nodes(node_map, k1, k2, k3)
+    K = sp.bsr_matrix((blocks, ci, rp), shape=(3 * nno, 3 * nno)).tocsr()
+    assert abs(K - K.T).max() == 0.0
+    u = rng.uniform(-1, 1, 3 * nno)
+    want = oracle.citcoms_n_assemble_del2_u(node_map, k1, k2, k3, u)
+    scale = abs(K) @ np.abs(u)
+    assert np.all(np.abs(K @ u - want) <= 1e-12 * scale + 1e-300)
+    for b in range(nno):  # rows sorted, diagonal present
+        cols = ci[rp[b]:rp[b + 1]]
+        assert np.all(np.diff(cols) > 0) and b in cols
+
+
+@FAST
+@given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9), st.integers(1, 5), st.integers(1, 5))
+def test_grid_pencil_order_is_a_permutation_with_consistent_tiles(n0, n1, n2, p0, p1):
+    n = n0 * n1 * n2
+    order = np.empty(n, dtype=np.int32)
+    nt_max = -(-n0 // p0) * -(-n1 // p1)
+    tiles = np.empty(nt_max + 1, dtype=np.int32)
+    nt = C.c_int()
+    assert L.g4s_grid_pencil_order(C.c_int(n0), C.c_int(n1), C.c_int(n2), C.c_int(p0), C.c_int(p1),
+                                   order.ctypes.data_as(C.c_void_p), tiles.ctypes.data_as(C.c_void_p), C.byref(nt)) == 0
+    assert nt.value == nt_max and tiles[0] == 0 and tiles[nt_max] == n and np.all(np.diff(tiles) > 0)
+    assert np.array_equal(np.sort(order), np.arange(n))
+    for t in range(nt_max):  # a tile is one patch of the first two axes, swept along the third
+        nodes = order[tiles[t]:tiles[t + 1]]
+        i, j, k = nodes % n0, (nodes // n0) % n1, nodes // (n0 * n1)
+        assert i.max() - i.min() < p0 and j.max() - j.min() < p1 and np.all(np.diff(k) >= 0)
