@@ -144,6 +144,10 @@ def cpu_spgemm(ref, oracle, grid):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # rank 0 runs alone (the other ranks have exited) and uses every host core it may: torchrun exports
+    # OMP_NUM_THREADS=1 to its children, which would turn the CPU arm into a single-thread number
+    if "LOCAL_RANK" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     from oracle.binding import Oracle
 
     oracle = Oracle()

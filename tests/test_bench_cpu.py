@@ -21,3 +21,24 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("SpMV y=Ax, 3-D 27-point Laplacian n=400")
+
+
+def test_reference_arm_under_torchrun_runs_on_rank0_with_all_cores():
+    """The driver launches the reference arm like ours (torchrun for N > 1): rank 0 alone prints the line, and it must not
+    inherit torchrun's OMP_NUM_THREADS=1."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
