@@ -5,7 +5,11 @@
 // Same accepted inputs, same resulting CSR (row-major (row, col) order, duplicates KEPT by the MatrixMarket
 // reader and SUMMED by the edge-list constructor); malformed input returns G4S_ERR_FORMAT / G4S_ERR_IO where
 // the reference throws std::runtime_error.  Outputs are malloc'd (g4s_free).
+#include <omp.h>
+#include <parallel/algorithm>
+
 #include <algorithm>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,25 +85,127 @@ int g4s_csr_read_matrix_market(const char *path, int *rows, int *cols, int *nnz,
         return fail(G4S_ERR_FORMAT, "MatrixMarket dimensions out of int32 range");
     if (E <= 0) return fail(G4S_ERR_FORMAT, "something wrong: nnz is 0");
 
-    std::vector<Entry> ent;
-    ent.reserve(general ? E : 2 * E);
-    long read = 0;
-    for (; read < E; ++read) {
-        long i, j;
-        double v = 1.0, imag;
-        if (!(in >> i >> j)) break;
-        if (!pattern && !(in >> v)) break;
-        if (complex_ && !(in >> imag)) break;
-        --i;
-        --j;
-        if (i < 0 || i >= R || j < 0 || j >= C) return fail(G4S_ERR_FORMAT, "MatrixMarket entry out of range");
-        ent.push_back({C * i + j, v});
-        if (!general && i != j) ent.push_back({C * j + i, skew ? -v : v});  // mirrored right after its source
+    // ---- body: a whitespace-separated TOKEN stream, T tokens per entry (the reference reads it with `in >> i >> j >> v`,
+    // so line breaks carry no meaning).  The rest of the file is read in one piece and tokenised / parsed by all cores:
+    // chunks are cut at token starts, a first pass counts the tokens of every chunk so that each chunk knows which
+    // entry its first token belongs to, a second pass parses the entries whose FIRST token lies in the chunk.
+    const int T = pattern ? 2 : (complex_ ? 4 : 3);
+    std::vector<char> text;
+    {
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        in.seekg(here);
+        text.resize((size_t)(end - here));
+        if (!text.empty() && !in.read(text.data(), (std::streamsize)text.size()))
+            return fail(G4S_ERR_IO, std::string("read error on \"") + path + "\"");
     }
-    if (read != E) return fail(G4S_ERR_FORMAT, "read nnz not equal to declared nnz " + std::to_string(read));
+    const char *buf = text.data();
+    const size_t len = text.size();
+    auto is_space = [](char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    const int nchunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)omp_get_max_threads() * 8, len / 65536 + 1));
+    std::vector<size_t> cut(nchunks + 1);
+    for (int c = 0; c <= nchunks; ++c) {
+        size_t p = len / nchunks * c;
+        if (c == nchunks) p = len;
+        while (p > 0 && p < len && !(is_space(buf[p - 1]) && !is_space(buf[p]))) ++p;  // move on to the next token start
+        cut[c] = p;
+    }
+    std::vector<long> tok0(nchunks + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < nchunks; ++c) {
+        long n = 0;
+        bool in_tok = false;
+        for (size_t p = cut[c]; p < cut[c + 1]; ++p) {
+            const bool sp_ = is_space(buf[p]);
+            n += (!sp_ && !in_tok);
+            in_tok = !sp_;
+        }
+        tok0[c + 1] = n;
+    }
+    for (int c = 0; c < nchunks; ++c) tok0[c + 1] += tok0[c];
+    const long avail = std::min<long>(E, tok0[nchunks] / T);  // complete entries present in the file
+    std::vector<long> I(avail), J(avail);
+    std::vector<double> V(pattern ? 0 : avail);
+    // integer token: [+-]digits, the whole token; value token: what `in >> double` accepts of the usual notations
+    auto parse_long = [](const char *b, const char *e, long &out) {
+        bool neg = false;
+        if (b < e && (*b == '+' || *b == '-')) neg = *b++ == '-';
+        if (b == e) return false;
+        long v = 0;
+        for (; b < e; ++b) {
+            if (*b < '0' || *b > '9') return false;
+            v = v * 10 + (*b - '0');
+        }
+        out = neg ? -v : v;
+        return true;
+    };
+    auto parse_double = [](const char *b, const char *e, double &out) {
+        if (b < e && *b == '+') ++b;
+        const auto r = std::from_chars(b, e, out);
+        return r.ec == std::errc() && r.ptr == e;
+    };
+    long first_bad = avail, first_range = avail;  // first entry that does not parse / lies outside the matrix
+#pragma omp parallel for schedule(dynamic, 1) reduction(min : first_bad, first_range)
+    for (int c = 0; c < nchunks; ++c) {
+        size_t p = cut[c];
+        long g = tok0[c];
+        while (p < cut[c + 1]) {
+            while (p < len && is_space(buf[p])) ++p;
+            if (p >= cut[c + 1]) break;
+            if (g % T != 0 || g / T >= avail) {  // not the first token of an entry we own: skip it
+                while (p < len && !is_space(buf[p])) ++p;
+                ++g;
+                continue;
+            }
+            const long k = g / T;
+            const char *tb[4], *te[4];
+            size_t q = p;
+            for (int t = 0; t < T; ++t) {  // the entry's tokens may run past this chunk's end
+                while (q < len && is_space(buf[q])) ++q;
+                tb[t] = buf + q;
+                while (q < len && !is_space(buf[q])) ++q;
+                te[t] = buf + q;
+            }
+            long i = 0, j = 0;
+            double v = 1.0, imag = 0.0;
+            bool ok = parse_long(tb[0], te[0], i) && parse_long(tb[1], te[1], j);
+            if (ok && !pattern) ok = parse_double(tb[2], te[2], v);
+            if (ok && complex_) ok = parse_double(tb[3], te[3], imag);
+            if (!ok) {
+                first_bad = std::min(first_bad, k);
+            } else {
+                --i;
+                --j;
+                if (i < 0 || i >= R || j < 0 || j >= C) first_range = std::min(first_range, k);
+                I[k] = i;
+                J[k] = j;
+                if (!pattern) V[k] = v;
+            }
+            while (p < len && !is_space(buf[p])) ++p;  // on to the token after the entry's first one
+            ++g;
+        }
+    }
+    if (first_range < first_bad) return fail(G4S_ERR_FORMAT, "MatrixMarket entry out of range");
+    if (first_bad != E) return fail(G4S_ERR_FORMAT, "read nnz not equal to declared nnz " + std::to_string(first_bad));
+    text = std::vector<char>();
+    // entries in file order, the mirror image of an off-diagonal entry of a symmetric file right after its source
+    std::vector<Entry> ent;
+    if (general) {
+        ent.resize(E);
+#pragma omp parallel for schedule(static)
+        for (long k = 0; k < E; ++k) ent[k] = {C * I[k] + J[k], pattern ? 1.0 : V[k]};
+    } else {
+        ent.reserve(2 * E);
+        for (long k = 0; k < E; ++k) {
+            const double v = pattern ? 1.0 : V[k];
+            ent.push_back({C * I[k] + J[k], v});
+            if (I[k] != J[k]) ent.push_back({C * J[k] + I[k], skew ? -v : v});
+        }
+    }
     if (ent.size() > 2147483647UL) return fail(G4S_ERR_FORMAT, "more than 2^31-1 entries after symmetric expansion");
     // (row, col) order.  The reference's std::sort leaves duplicates in unspecified order; file order is kept here.
-    std::stable_sort(ent.begin(), ent.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
+    __gnu_parallel::stable_sort(ent.begin(), ent.end(), [](const Entry &a, const Entry &b) { return a.key < b.key; });
 
     std::vector<int> rp(R + 1, 0), ci(ent.size());
     std::vector<double> va(ent.size());
