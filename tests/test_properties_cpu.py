@@ -102,3 +102,55 @@ def test_grid_pencil_order_is_a_permutation_with_consistent_tiles(n0, n1, n2, p0
         nodes = order[tiles[t]:tiles[t + 1]]
         i, j, k = nodes % n0, (nodes // n0) % n1, nodes // (n0 * n1)
         assert i.max() - i.min() < p0 and j.max() - j.min() < p1 and np.all(np.diff(k) >= 0)
+
+
+def test_matrix_market_reader_token_stream_semantics(oracle, tmp_path):
+    """The reference reads the body with `in >> i >> j >> v`: a token stream in which line breaks mean nothing.  Randomly
+    formatted files (entries spanning lines, several per line, tabs / CRLF, '+' signs, exponent notations, duplicates, every
+    banner kind) must give the oracle's CSR bit for bit through the parallel parser."""
+    rng = np.random.default_rng(0)
+    kinds = ["real general", "real symmetric", "pattern general", "integer general", "complex general",
+             "real skew-symmetric", "pattern symmetric"]
+    seps = [" ", "\n", "\t", "  \n", "\r\n", " \t "]
+    checked = 0
+    for trial in range(84):
+        kind = kinds[trial % len(kinds)]
+        sym = "general" not in kind
+        R = int(rng.integers(1, 30))
+        Cc = R if sym else int(rng.integers(1, 30))
+        entries = []
+        for _ in range(int(rng.integers(1, 60))):
+            i, j = int(rng.integers(1, R + 1)), int(rng.integers(1, Cc + 1))
+            if sym and j > i:
+                i, j = j, i
+            if "skew" in kind and i == j:
+                continue
+            ent = [("+%d" % i) if rng.random() < 0.1 else str(i), str(j)]
+            if "pattern" not in kind:
+                v = rng.uniform(-5, 5)
+                fmt = ["%r", "%.3e", "%.17g", "%+.5f"][int(rng.integers(0, 4))]
+                ent.append(str(int(v * 10)) if "integer" in kind else fmt % v)
+            if "complex" in kind:
+                ent.append("%.2f" % rng.uniform(-1, 1))
+            entries.append(ent)
+        if not entries:
+            continue
+        body = "".join(tok + seps[int(rng.integers(0, len(seps)))] for ent in entries for tok in ent)
+        p = str(tmp_path / "fuzz.mtx")
+        with open(p, "w", newline="") as fh:
+            fh.write("%%MatrixMarket matrix coordinate " + kind + "\n%c\n" + "%d %d %d\n" % (R, Cc, len(entries)) + body)
+        want = oracle.mm_construct(p)
+        got = g4s_b200.CSR.construct(p)
+        assert (got.rows, got.cols) == want[:2]
+        assert np.array_equal(got.rowptr, want[2]) and np.array_equal(got.colids, want[3])
+        assert np.array_equal(got.values.view(np.int64), np.asarray(want[4]).view(np.int64))
+        checked += 1
+    assert checked > 70
+    # one token short: the count error of the reference, not a crash
+    with open(p, "w") as fh:
+        fh.write("%%MatrixMarket matrix coordinate real general\n3 3 2\n1 1 1.0\n2 2\n")
+    try:
+        g4s_b200.CSR.construct(p)
+        raise AssertionError("accepted a truncated file")
+    except g4s_b200.G4SError as e:
+        assert e.status == -5 and "read nnz not equal to declared nnz 1" in str(e)
