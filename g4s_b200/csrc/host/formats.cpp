@@ -230,36 +230,60 @@ int g4s_csr_from_edge_list(long m, long n, const long *start, const long *end, c
     if (m < 0 || n < 0 || (m > 0 && (!start || !end || !w)) || !nnz || !rowptr || !colids || !values)
         return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: bad arguments");
     if (n > 2147483646L) return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: more than 2^31-2 vertices");
-    for (long e = 0; e < m; ++e)
-        if (start[e] < 0 || start[e] >= n || end[e] < 0 || end[e] >= n)
-            return fail(G4S_ERR_FORMAT, "g4s_csr_from_edge_list: vertex id out of range");
+    bool in_range = true;
+#pragma omp parallel for schedule(static) reduction(&& : in_range)
+    for (long e = 0; e < m; ++e) in_range = in_range && start[e] >= 0 && start[e] < n && end[e] >= 0 && end[e] < n;
+    if (!in_range) return fail(G4S_ERR_FORMAT, "g4s_csr_from_edge_list: vertex id out of range");
     // Runs of equal start vertex are sorted by (end, weight) and equal (start, end) pairs are summed left to
-    // right; a start vertex that shows up again later opens a new, unmerged run — as in the reference.
-    typedef std::pair<std::pair<long, long>, double> Edge;
-    std::vector<Edge> run, merged;
-    merged.reserve(static_cast<size_t>(m));
-    long e = 0;
-    while (e < m) {
-        run.clear();
-        const long s = start[e];
-        for (; e < m && start[e] == s; ++e) run.push_back(Edge(std::make_pair(s, end[e]), w[e]));
-        std::sort(run.begin(), run.end());
-        merged.push_back(run[0]);
-        for (size_t k = 1; k < run.size(); ++k) {
-            if (run[k].first == run[k - 1].first) merged.back().second += run[k].second;
-            else merged.push_back(run[k]);
+    // right; a start vertex that shows up again later opens a new, unmerged run — as in the reference.  The runs are
+    // independent, so they are sorted and merged by all cores (in place, in a copy of the (end, weight) pairs); one
+    // sequential pass over the RUNS then places them row by row in order of appearance.
+    typedef std::pair<long, double> Half;  // (end, weight): the start vertex is the same throughout a run
+    std::vector<long> run_begin;
+    for (long e = 0; e < m; ++e)
+        if (e == 0 || start[e] != start[e - 1]) run_begin.push_back(e);
+    const long nruns = (long)run_begin.size();
+    run_begin.push_back(m);
+    std::vector<Half> half(static_cast<size_t>(m));
+#pragma omp parallel for schedule(static)
+    for (long e = 0; e < m; ++e) half[e] = Half(end[e], w[e]);
+    std::vector<long> kept(nruns + 1, 0);  // entries of a run after merging
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < nruns; ++r) {
+        Half *b = half.data() + run_begin[r], *e = half.data() + run_begin[r + 1];
+        std::sort(b, e);
+        Half *out = b;
+        for (Half *q = b + 1; q < e; ++q) {
+            if (q->first == out->first) out->second += q->second;
+            else *++out = *q;
         }
+        kept[r] = out - b + 1;
     }
-    if (merged.size() > 2147483647UL) return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: nnz exceeds int32");
-    std::vector<int> rp(n + 1, 0), ci(merged.size());
-    std::vector<double> va(merged.size());
-    for (const Edge &t : merged) rp[t.first.first + 1]++;
+    std::vector<int> rp(n + 1, 0);
+    std::vector<long> place(nruns);  // position of the run inside its row
+    long total = 0;
+    for (long r = 0; r < nruns; ++r) {
+        const long row = start[run_begin[r]];
+        place[r] = rp[row + 1];
+        rp[row + 1] += (int)kept[r];
+        total += kept[r];
+        if (total > 2147483647L) return fail(G4S_ERR_INVALID, "g4s_csr_from_edge_list: nnz exceeds int32");
+    }
     for (long r = 0; r < n; ++r) rp[r + 1] += rp[r];
-    std::vector<int> cursor(rp.begin(), rp.end() - 1);
-    for (const Edge &t : merged) {
-        const int pos = cursor[t.first.first]++;
-        ci[pos] = static_cast<int>(t.first.second);
-        va[pos] = t.second;
+    struct Merged {
+        size_t n;
+        size_t size() const { return n; }
+    } merged{static_cast<size_t>(total)};
+    std::vector<int> ci(merged.size());
+    std::vector<double> va(merged.size());
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < nruns; ++r) {
+        const Half *b = half.data() + run_begin[r];
+        const long at = rp[start[run_begin[r]]] + place[r];
+        for (long k = 0; k < kept[r]; ++k) {
+            ci[at + k] = static_cast<int>(b[k].first);
+            va[at + k] = b[k].second;
+        }
     }
     *nnz = static_cast<int>(merged.size());
     *rowptr = to_malloc(rp);
