@@ -11,6 +11,8 @@
 // Equation numbers are 3*(node-1)+direction (construct_id, Construct_arrays.c:156-160), so node b is block row b.
 // The BSR built here stores BOTH triangles (the GPU kernel streams whole block rows and has no scatter), rows sorted by
 // block column, values widened to fp64 (the reference's higher_precision is float, global_defs.h:116-120).
+#include <omp.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -32,25 +34,47 @@ template <class T>
 int convert(int nno, const int *node_map, const T *k1, const T *k2, const T *k3, int *nnzb, int **browptr_out,
             int **bcolids_out, double **bvalues_out) {
     const long long neq = 3LL * nno;
-    // pass 1: validate the map, count the lower neighbours of every node and how often it is somebody's neighbour
+    // pass 1 (all cores): validate the map, count the lower neighbours of every node and how often it is somebody's
+    // neighbour, and find the largest distance between a node and a neighbour it names (bounds the scan of pass 2)
     std::vector<int> lower(nno, 0), upper(nno, 0);
+    int first_bad = nno, reach = 0;
+#pragma omp parallel for schedule(static) reduction(min : first_bad) reduction(max : reach)
     for (int b = 0; b < nno; ++b) {
         const int *c = node_map + (size_t)b * kMaxEqn;
-        for (int d = 0; d < 3; ++d)
-            if (c[d] != 3 * b + d) return fail(G4S_ERR_FORMAT, "node map: node " + std::to_string(b + 1) + " does not own equations 3(node-1)+d");
-        for (int ia = 1; ia < kSlots; ++ia) {
+        bool ok = true;
+        for (int d = 0; d < 3; ++d) ok = ok && c[d] == 3 * b + d;
+        int nl = 0;
+        for (int ia = 1; ok && ia < kSlots; ++ia) {
             const int e0 = c[3 * ia];
             if (e0 == neq) {
-                if (c[3 * ia + 1] != neq || c[3 * ia + 2] != neq)
-                    return fail(G4S_ERR_FORMAT, "node map: half-used slot at node " + std::to_string(b + 1));
+                ok = c[3 * ia + 1] == neq && c[3 * ia + 2] == neq;
                 continue;
             }
-            if (e0 < 0 || e0 % 3 != 0 || c[3 * ia + 1] != e0 + 1 || c[3 * ia + 2] != e0 + 2 || e0 / 3 >= b)
-                return fail(G4S_ERR_FORMAT, "node map: slot " + std::to_string(ia) + " of node " + std::to_string(b + 1) +
-                                                " is not the three equations of a lower-numbered node");
-            ++lower[b];
+            ok = e0 >= 0 && e0 % 3 == 0 && c[3 * ia + 1] == e0 + 1 && c[3 * ia + 2] == e0 + 2 && e0 / 3 < b;
+            if (!ok) break;
+            ++nl;
+            reach = std::max(reach, b - e0 / 3);
+#pragma omp atomic
             ++upper[e0 / 3];
         }
+        if (!ok) first_bad = std::min(first_bad, b);
+        lower[b] = nl;
+    }
+    if (first_bad < nno) {  // name the defect of the first offending node (sequential re-check of that node only)
+        const int b = first_bad;
+        const int *c = node_map + (size_t)b * kMaxEqn;
+        for (int d = 0; d < 3; ++d)
+            if (c[d] != 3 * b + d)
+                return fail(G4S_ERR_FORMAT, "node map: node " + std::to_string(b + 1) + " does not own equations 3(node-1)+d");
+        for (int ia = 1; ia < kSlots; ++ia) {
+            const int e0 = c[3 * ia];
+            if (e0 == neq && (c[3 * ia + 1] != neq || c[3 * ia + 2] != neq))
+                return fail(G4S_ERR_FORMAT, "node map: half-used slot at node " + std::to_string(b + 1));
+            if (e0 != neq && (e0 < 0 || e0 % 3 != 0 || c[3 * ia + 1] != e0 + 1 || c[3 * ia + 2] != e0 + 2 || e0 / 3 >= b))
+                return fail(G4S_ERR_FORMAT, "node map: slot " + std::to_string(ia) + " of node " + std::to_string(b + 1) +
+                                                " is not the three equations of a lower-numbered node");
+        }
+        return fail(G4S_ERR_FORMAT, "node map: malformed entry at node " + std::to_string(b + 1));
     }
     long long total = 0;
     for (int b = 0; b < nno; ++b) total += 1 + lower[b] + upper[b];
@@ -66,43 +90,60 @@ int convert(int nno, const int *node_map, const T *k1, const T *k2, const T *k3,
     }
     rp[0] = 0;
     for (int b = 0; b < nno; ++b) rp[b + 1] = rp[b] + 1 + lower[b] + upper[b];
-    // pass 2: nodes in ascending order.  Row b = [its lower neighbours, sorted][itself][nodes that name b, ascending
-    // because they arrive in ascending order]
-    std::vector<int> cursor(nno);  // next free upper position of every row
-    for (int b = 0; b < nno; ++b) cursor[b] = rp[b] + lower[b] + 1;
-    int order[kSlots];
-    for (int b = 0; b < nno; ++b) {
-        const int *c = node_map + (size_t)b * kMaxEqn;
-        const T *B[3] = {k1 + (size_t)b * kMaxEqn, k2 + (size_t)b * kMaxEqn, k3 + (size_t)b * kMaxEqn};
-        int nl = 0;
-        for (int ia = 1; ia < kSlots; ++ia)
-            if (c[3 * ia] != neq) order[nl++] = ia;
-        std::sort(order, order + nl, [&](int x, int y) { return c[3 * x] < c[3 * y]; });
-        int pos = rp[b];
-        for (int q = 0; q < nl; ++q, ++pos) {
-            const int ia = order[q], n = c[3 * ia] / 3;
-            if (q && n == c[3 * order[q - 1]] / 3) {
-                free(rp);
-                free(ci);
-                free(va);
-                return fail(G4S_ERR_FORMAT, "node map: node " + std::to_string(b + 1) + " lists a neighbour twice");
+    // pass 2 (all cores): block rows are dealt out in contiguous stretches.  The owner of rows [r0, r1) writes, for each of
+    // them, [its lower neighbours, sorted][itself], and then walks the nodes e in (r0, r1 + reach) in ascending order and
+    // appends the transposed block of every neighbour of e that lies in [r0, r1) — ascending e, so the upper part of a row
+    // comes out sorted without a sort.
+    const int nchunks = std::max(1, std::min(nno / 4096 + 1, omp_get_max_threads() * 4));
+    int twice = nno;  // first node that lists a neighbour twice
+#pragma omp parallel for schedule(dynamic, 1) reduction(min : twice)
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int r0 = (int)((long long)nno * ch / nchunks), r1 = (int)((long long)nno * (ch + 1) / nchunks);
+        std::vector<int> cursor(r1 - r0);  // next free upper position of every owned row
+        int order[kSlots];
+        for (int b = r0; b < r1; ++b) {
+            cursor[b - r0] = rp[b] + lower[b] + 1;
+            const int *c = node_map + (size_t)b * kMaxEqn;
+            const T *B[3] = {k1 + (size_t)b * kMaxEqn, k2 + (size_t)b * kMaxEqn, k3 + (size_t)b * kMaxEqn};
+            int nl = 0;
+            for (int ia = 1; ia < kSlots; ++ia)
+                if (c[3 * ia] != neq) order[nl++] = ia;
+            std::sort(order, order + nl, [&](int x, int y) { return c[3 * x] < c[3 * y]; });
+            int pos = rp[b];
+            for (int q = 0; q < nl; ++q, ++pos) {
+                const int ia = order[q];
+                if (q && c[3 * ia] == c[3 * order[q - 1]]) twice = std::min(twice, b);
+                ci[pos] = c[3 * ia] / 3;
+                double *blk = va + (size_t)pos * 9;  // K[3b+k][3n+d]
+                for (int k = 0; k < 3; ++k)
+                    for (int d = 0; d < 3; ++d) blk[3 * k + d] = (double)B[k][3 * ia + d];
             }
-            ci[pos] = n;
-            double *blk = va + (size_t)pos * 9;  // K[3b+k][3n+d]
-            const int up = cursor[n]++;
-            ci[up] = b;
-            double *tblk = va + (size_t)up * 9;  // K[3n+d][3b+k], the same coefficient
-            for (int k = 0; k < 3; ++k)
-                for (int d = 0; d < 3; ++d) {
-                    const double v = (double)B[k][3 * ia + d];
-                    blk[3 * k + d] = v;
-                    tblk[3 * d + k] = v;
-                }
+            ci[pos] = b;
+            double *diag = va + (size_t)pos * 9;  // K[3b+i][3b+k] = Eqn_k{k+1}[i]
+            for (int i = 0; i < 3; ++i)
+                for (int k = 0; k < 3; ++k) diag[3 * i + k] = (double)B[k][i];
         }
-        ci[pos] = b;
-        double *diag = va + (size_t)pos * 9;  // K[3b+i][3b+k] = Eqn_k{k+1}[i]
-        for (int i = 0; i < 3; ++i)
-            for (int k = 0; k < 3; ++k) diag[3 * i + k] = (double)B[k][i];
+        const int e_end = (int)std::min<long long>(nno, (long long)r1 + reach);
+        for (int e = r0 + 1; e < e_end; ++e) {
+            const int *c = node_map + (size_t)e * kMaxEqn;
+            const T *B[3] = {k1 + (size_t)e * kMaxEqn, k2 + (size_t)e * kMaxEqn, k3 + (size_t)e * kMaxEqn};
+            for (int ia = 1; ia < kSlots; ++ia) {
+                if (c[3 * ia] == neq) continue;
+                const int n = c[3 * ia] / 3;
+                if (n < r0 || n >= r1) continue;
+                const int up = cursor[n - r0]++;
+                ci[up] = e;
+                double *tblk = va + (size_t)up * 9;  // K[3n+d][3e+k] = K[3e+k][3n+d]
+                for (int k = 0; k < 3; ++k)
+                    for (int d = 0; d < 3; ++d) tblk[3 * d + k] = (double)B[k][3 * ia + d];
+            }
+        }
+    }
+    if (twice < nno) {
+        free(rp);
+        free(ci);
+        free(va);
+        return fail(G4S_ERR_FORMAT, "node map: node " + std::to_string(twice + 1) + " lists a neighbour twice");
     }
     *nnzb = (int)total;
     *browptr_out = rp;
