@@ -131,7 +131,7 @@ int g4s_csr_read_matrix_market(const char *path, int *rows, int *cols, int *nnz,
     auto parse_long = [](const char *b, const char *e, long &out) {
         bool neg = false;
         if (b < e && (*b == '+' || *b == '-')) neg = *b++ == '-';
-        if (b == e) return false;
+        if (b == e || e - b > 18) return false;  // 18 digits cannot overflow a long
         long v = 0;
         for (; b < e; ++b) {
             if (*b < '0' || *b > '9') return false;
