@@ -154,3 +154,16 @@ def test_matrix_market_reader_token_stream_semantics(oracle, tmp_path):
         raise AssertionError("accepted a truncated file")
     except g4s_b200.G4SError as e:
         assert e.status == -5 and "read nnz not equal to declared nnz 1" in str(e)
+
+
+@FAST
+@given(st.integers(1, 7), st.integers(1, 7), st.integers(1, 9), st.data())
+def test_grid_pencil_order_local_covers_a_rank_slab(n0, n1, n2, data):
+    """The schedule of one rank of a row-partitioned mesh matrix: a permutation of its LOCAL rows, whatever the cut."""
+    from g4s_b200.dist import grid_pencil_order_local
+
+    n = n0 * n1 * n2
+    row0 = data.draw(st.integers(0, n - 1))
+    row1 = data.draw(st.integers(row0 + 1, n))
+    order = grid_pencil_order_local(n0, n1, n2, row0, row1, p0=3, p1=2)
+    assert order.dtype == np.int32 and np.array_equal(np.sort(order), np.arange(row1 - row0))
