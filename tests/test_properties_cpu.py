@@ -167,3 +167,21 @@ def test_grid_pencil_order_local_covers_a_rank_slab(n0, n1, n2, data):
     row1 = data.draw(st.integers(row0 + 1, n))
     order = grid_pencil_order_local(n0, n1, n2, row0, row1, p0=3, p1=2)
     assert order.dtype == np.int32 and np.array_equal(np.sort(order), np.arange(row1 - row0))
+
+
+@FAST
+@given(st.integers(1, 40), st.integers(0, 400), st.integers(0, 2 ** 31 - 1), st.booleans())
+def test_edge_list_constructor_equals_oracle(oracle, n, m, seed, grouped):
+    """CSR(graph&) (mm/inc/CSR.h:255-329): runs of equal start vertex are sorted by (end, weight) and duplicates summed left
+    to right; a start vertex that comes back later opens a new, unmerged run.  The parallel constructor must give the oracle's
+    arrays bit for bit, grouped input or not."""
+    rng = np.random.default_rng(seed)
+    start = rng.integers(0, n, m).astype(np.int64)
+    if grouped:
+        start = np.sort(start)
+    end = rng.integers(0, n, m).astype(np.int64)
+    w = rng.integers(-4, 5, m).astype(np.float64) * 0.25 + rng.uniform(0, 1e-3, m)
+    got = g4s_b200.CSR.from_graph(n, start, end, w)
+    want = oracle.csr_from_graph(n, start, end, w)[-3:]
+    assert np.array_equal(got.rowptr, want[0]) and np.array_equal(got.colids, want[1])
+    assert np.array_equal(got.values.view(np.int64), np.asarray(want[2]).view(np.int64))
