@@ -73,6 +73,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line)
 
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi takes up to a second to attach to every GPU of the box; the timed region must not start while
+        it does (its start-up was inside the 10-20 ms timed region of the multi-GPU runs of round 1)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -168,6 +175,89 @@ def run_reference(args, rank):
     emit(line)
 
 
+# ----------------------------------------------------------------------------------------------- parity inside the bench
+def det_x_numpy(idx):
+    """x as a function of the GLOBAL index (exact in fp64): any rank and the CPU checker can regenerate any entry."""
+    h = (idx.astype(np.uint64) * np.uint64(2654435761) + np.uint64(12345)) & np.uint64(0xFFFFFFFF)
+    return h.astype(np.float64) / 4294967296.0 - 0.5
+
+
+def det_x_torch(torch, lo, hi, device):
+    idx = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    h = (idx * 2654435761 + 12345) & 0xFFFFFFFF
+    return h.to(torch.float64) / 4294967296.0 - 0.5
+
+
+def spmv_parity_check(torch, dist, n, c0, c1, product, world, rank):
+    """Correctness of the very operator that was timed, on the box it was timed on:
+      (1) x = 1  =>  y[r] = 27 - (#stencil points of row r), exactly, for EVERY owned row (closed form of the matrix);
+      (2) x = det_x(global index): stretches of owned rows — always including both ends of the rank's range, where
+          the entries of x live on the neighbouring GPUs — against the oracle's CSR row loop on rows regenerated on
+          the CPU, tolerance 1e-12 * sum_j |a_ij x_j|.
+    `product(x_local_tensor) -> y_local_tensor` runs one product.  Returns the "parity_check" block (all ranks)."""
+    from oracle.binding import Oracle
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = c1 - c0
+    y = product(torch.ones(rows, dtype=torch.float64, device=dev))
+    r = torch.arange(c0, c1, dtype=torch.int64, device=dev)
+    cnt = torch.ones(rows, dtype=torch.int64, device=dev)
+    for q in (r % n, (r // n) % n, r // (n * n)):
+        cnt *= 3 - ((q == 0) | (q == n - 1)).to(torch.int64)
+    del r, q
+    bad_ones = int((y != (27 - cnt).to(torch.float64)).sum().item())
+    del cnt
+    y = product(det_x_torch(torch, c0, c1, dev))
+    oracle = Oracle()
+    stretch = 4096
+    nstretch = max(2, -(-26 // world))
+    starts = sorted(set(int(v) for v in np.linspace(c0, max(c0, c1 - stretch), nstretch)))
+    checked, worst = 0, 0.0
+    for r0 in starts:
+        r1 = min(r0 + stretch, c1)
+        A = oracle.gen_laplacian3d27(n, r0, r1)
+        lo, hi = int(A[3].min()), int(A[3].max()) + 1
+        xw = det_x_numpy(np.arange(lo, hi, dtype=np.int64))
+        col = (A[3] - lo).astype(np.int32)
+        want = oracle.spmv_csr(A[2], col, A[4], xw)
+        scale = oracle.spmv_csr_abs(A[2], col, A[4], xw)
+        got = y[r0 - c0:r1 - c0].cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(scale, 1e-300))))
+        checked += r1 - r0
+    t = torch.tensor([float(bad_ones), float(checked), float(rows)], dtype=torch.float64, device=dev)
+    w = torch.tensor([worst], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    bad_ones, checked, rows_all, worst = int(t[0].item()), int(t[1].item()), int(t[2].item()), float(w.item())
+    return {"ok": bad_ones == 0 and worst <= 1e-12,
+            "ones_closed_form": {"rows": rows_all, "mismatches": bad_ones, "rule": "y = 27 - #stencil points, exact"},
+            "sampled_vs_oracle": {"rows": checked, "max_err_over_abs_row_sum": worst, "tolerance": 1e-12,
+                                  "x": "det_x(global index)", "stretches_per_rank": len(starts)}}
+
+
+def per_step_times(torch, dist, step, steps, barrier):
+    """Diagnostic pass AFTER the timed region: one CUDA event per step, per-rank median / p90 / max / first."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+    mine = torch.tensor([float(np.median(ms)), float(np.percentile(ms, 90)), float(ms.max()), float(ms[0]), float(ms.sum())],
+                        dtype=torch.float64, device="cuda")
+    if dist is not None:
+        every = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(every, mine)
+    else:
+        every = [mine]
+    keys = ("median", "p90", "max", "first", "sum")
+    return {"note": "separate pass after the timed region, one event per step; per rank",
+            **{k: [round(float(e[i].item()), 5) for e in every] for i, k in enumerate(keys)}}
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world):
     import torch
@@ -258,12 +348,13 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:  # running (attached to every GPU) well before the timed region starts
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = L.g4s_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -301,6 +392,32 @@ def run_ours(args, rank, world):
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = total_bytes / (e2e_s / args.steps) / 1e9
 
+    # correctness of the operator that was just timed + a per-step look at the same loop (both outside the timed regions)
+    if world == 1:
+        c0, c1 = 0, rows_total
+
+        def product(xt):
+            A.spmv_device(xt.data_ptr(), y.data_ptr())
+            return y
+    else:
+        c0, c1 = op.c0, op.c1
+
+        def product(xt):
+            if op.mode == "peer":
+                xb = op.next_x()  # no barrier: the kernel's own flag protocol orders the peers' reads after this copy
+                xb.copy_(xt)
+                return op.apply(xb, y)
+            return op.apply(xt, y)
+    step_ms = per_step_times(torch, dist, step, args.steps, barrier)
+    parity = None
+    if not args.no_parity:
+        parity = spmv_parity_check(torch, dist, n, c0, c1, product, world, rank)
+        if world > 1 and op.mode == "peer":  # leave the shared buffers as the timed loop had them
+            for xb in op.x_buffers:
+                xb.copy_(x)
+            torch.cuda.synchronize()
+            dist.barrier()
+
     spgemm_multi = None
     if dist is not None and not args.no_spgemm:
         spgemm_multi = bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world)
@@ -337,6 +454,8 @@ def run_ours(args, rank, world):
                         "in the reference's mkl()); every step uploads x from pinned host memory and downloads y; "
                         "the call pipelines upload / row-block products / download on three streams"},
         "gpu_launches": int(launches),
+        "step_ms": step_ms,
+        "parity_check": parity,
         "roofline": {"bound": "hbm", "kernel": "spmv_chunk_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic},
     }
@@ -364,6 +483,8 @@ def run_ours(args, rank, world):
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("parity check of the timed operator FAILED: %s" % json.dumps(parity))
 
 
 def bench_other_configs(g4s_b200, torch, peak):
@@ -474,7 +595,27 @@ def bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world):
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t)
     ms, flop = float(tmax[0].item()), float(t[1].item())
+    # parity of the distributed product through closed forms of A*A on the 5-point Laplacian:
+    # nnz = 13 n^2 - 20 n + 4, sum of all entries = 4 n + 8, every local row's columns strictly ascending
+    from g4s_b200.dist import _DevArray
+    Cl, _ = mm.multiply()
+    rp, ci, va = Cl.device_arrays()
+    vals = torch.as_tensor(_DevArray(va, Cl.nnz, "<f8"), device="cuda")
+    cols = torch.as_tensor(_DevArray(ci, Cl.nnz, "<i4"), device="cuda")
+    rpt = torch.as_tensor(_DevArray(rp, Cl.rows + 1, "<i4"), device="cuda").long()
+    inner = torch.ones(Cl.nnz, dtype=torch.bool, device="cuda")
+    inner[rpt[1:-1][rpt[1:-1] < Cl.nnz]] = False          # first entry of a row: no left neighbour in the same row
+    unsorted = int(((cols[1:] <= cols[:-1]) & inner[1:]).sum().item())
+    chk = torch.tensor([float(Cl.nnz), float(vals.sum().item()), float(unsorted)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(chk)
+    Cl.make_empty()
+    want_nnz, want_sum = 13 * n * n - 20 * n + 4, 4.0 * n + 8.0
+    parity = {"ok": int(chk[0].item()) == want_nnz and abs(float(chk[1].item()) - want_sum) <= 1e-9 * want_sum
+              and int(chk[2].item()) == 0,
+              "global_nnz": int(chk[0].item()), "want_nnz": want_nnz, "sum_of_values": float(chk[1].item()),
+              "want_sum": want_sum, "rows_with_unsorted_columns": int(chk[2].item())}
     return {"metric": "spgemm_gflops", "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms": ms, "n_gpus": world,
+            "parity_check": parity,
             "config": {"workload": "SpGEMM C=A*A, 2-D 5-point Laplacian n=%d (BASELINE configs[3]); A row-partitioned, "
                                    "B replicated by NCCL broadcast (%.1f ms, once), C left distributed" % (n, bcast_s * 1e3),
                        "nnzC": mm.global_nnz, "flop": flop}}
@@ -531,6 +672,7 @@ def main():
     ap.add_argument("--mode", default="peer", choices=["peer", "halo", "allgather", "auto"],
                     help="multi-GPU x assembly (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity check of the timed operator")
     ap.add_argument("--no-spgemm", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the single-GPU riders for configs[0], [2], [4]")
     args = ap.parse_args()

@@ -448,10 +448,10 @@ int g4s_bsr3_spmm64_partitioned_ordered_device(int mb_local, const int *browptr_
     if (mb_local == 0) return G4S_OK;
     if ((rc = ensure_device())) return rc;
     auto k = bsr3_spmm64_kpack_ordered_kernel<true>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needs()) {
         G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-        configured = true;
+        configured.done();
     }
     const int grid = (int)std::min<long long>(((long long)mb_local + 15) / 16, (long long)sm_count());
     k<<<grid, 512, 0, (cudaStream_t)stream>>>(mb_local, row_order_dev, nullptr, grid, browptr_dev, bcolids_dev, bvalues_dev,
@@ -470,10 +470,10 @@ int g4s_bsr3_spmm64_ordered_device(int mb, int kb, const int *browptr_dev, const
     int rc = ensure_device();
     if (rc) return rc;
     auto k = bsr3_spmm64_kpack_ordered_kernel<false>;
-    static bool configured = false;
-    if (!configured) {  // no shared memory: the whole carve-out is L1
+    static PerDeviceOnce configured;
+    if (configured.needs()) {  // no shared memory: the whole carve-out is L1
         G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-        configured = true;
+        configured.done();
     }
     if (tile_ptr_dev && ntiles < 1) return fail(G4S_ERR_INVALID, "g4s_bsr3_spmm64_ordered_device: tile_ptr without tiles");
     const int grid = (int)std::min<long long>(tile_ptr_dev ? ntiles : ((long long)mb + 15) / 16, (long long)sm_count());

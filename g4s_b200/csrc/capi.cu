@@ -381,7 +381,7 @@ int g4s_spmv_partitioned_device(g4s_csr_t A, int world, int self, const double *
 
 int g4s_spmv_partition_info(g4s_csr_t A, int *n_remote_columns, unsigned *owner_mask) {
     if (!A) return fail(G4S_ERR_INVALID, "null handle");
-    if (n_remote_columns) *n_remote_columns = A->localized ? A->plan.part_n_needed : -1;
+    if (n_remote_columns) *n_remote_columns = A->plan.part_colids ? A->plan.part_n_needed : -1;
     if (owner_mask) *owner_mask = A->plan.part_owner_mask;
     return G4S_OK;
 }

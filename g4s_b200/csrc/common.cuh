@@ -35,6 +35,27 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 int ensure_device();  // G4S_OK when the current device is usable (sm_100), else G4S_ERR_CUDA
 int sm_count();
 
+// cudaFuncSetAttribute state is per device: a once-per-process flag would leave every kernel that needs > 48 KB of dynamic
+// shared memory unconfigured on the second device a process uses.  One slot per device, holding the value the attribute
+// was last set for (key) — a launch with another key (e.g. another shared-memory carve-out for the same instantiation)
+// configures again.  Thread-safe: concurrent first launches at worst both set the same attributes.
+struct PerDeviceOnce {
+    std::atomic<int> key[64];
+    PerDeviceOnce() {
+        for (auto &k : key) k.store(-1, std::memory_order_relaxed);
+    }
+    // true when the caller must (re)configure for `want` on the current device
+    bool needs(int want = 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        return key[dev].load(std::memory_order_acquire) != want;
+    }
+    void done(int want = 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) key[dev].store(want, std::memory_order_release);
+    }
+};
+
 // ---- the CSR handle ---------------------------------------------------------------------------------
 struct SpmvPlan {
     int cap = 0;                        // max nonzeros per chunk
@@ -44,7 +65,8 @@ struct SpmvPlan {
     double *carry = nullptr;            // [nchunks]   partial sums of non-final pieces of long rows
     int4 *long_rows = nullptr;          // [n_long]    (row, first chunk, pieces, -)
     unsigned char *part_flags = nullptr;  // [nchunks] partitioned x: chunk references a remote column
-    int *part_needed = nullptr;           // localized handle: global column of halo entry k (ascending)
+    int *part_colids = nullptr;           // [nnz] private copy of the column ids with remote columns rewritten to -1 - k
+    int *part_needed = nullptr;           // localized plan: global column of halo entry k (ascending)
     int part_n_needed = 0;
     double *part_halo = nullptr;          // [part_n_needed] remote x entries, refilled by every partitioned product
     unsigned long long *part_halo_done = nullptr;  // gather warps that have published their share, over all products
@@ -71,7 +93,6 @@ struct g4s_csr {
     int *colids = nullptr;
     double *values = nullptr;
     bool owns = false;
-    bool localized = false;  // column ids outside the owned range were rewritten to -1 - k by a partitioned product
     int sorted_cols = -1;  // -1 unknown, 1 every row's column ids strictly ascending, 0 not (SpGEMM merge class)
     bool pooled = false;  // arrays came from cudaMallocAsync (stream-ordered pool) rather than cudaMalloc
     g4s::SpmvPlan plan;

@@ -860,10 +860,10 @@ static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, cudaStre
     const size_t smem = NUMERIC ? sizeof(double) * (RPC * TABLE + RPC * WMAX) + sizeof(int) * (RPC * TABLE + RPC * WMAX + RPC) + 16
                                 : sizeof(int) * (RPC * TABLE + RPC) + 16;
     auto k = spgemm_smem_kernel<GROUP, TABLE, WMAX, THREADS, NUMERIC>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needs()) {
         G4S_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.done();
     }
     const long long want = ((long long)nlist + RPC - 1) / RPC;
     const int grid = (int)std::min<long long>(want, (long long)sm_count() * 16);
@@ -879,11 +879,11 @@ static int launch_thread_row(const SpgemmArgs &a, const int *list, int nlist, bo
     const size_t smem_num = (sizeof(int) + sizeof(double)) * TABLE * THREADS;
     auto ks = spgemm_thread_row_kernel<TABLE, THREADS, false>;
     auto kn = spgemm_thread_row_kernel<TABLE, THREADS, true>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needs()) {
         G4S_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sym));
         G4S_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_num));
-        configured = true;
+        configured.done();
     }
     const long long want = ((long long)nlist + THREADS - 1) / THREADS;
     const int grid = (int)std::min<long long>(want, (long long)sm_count() * 32);
@@ -1031,12 +1031,12 @@ static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool nume
     Workspace &ws = t_ws;
     const int nwords = (a.N + 31) / 32;
     const size_t smem = sizeof(unsigned) * ((size_t)nwords + 34);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.needs()) {
         const int cap = (int)(sizeof(unsigned) * (SPA_MAX_COLS / 32 + 34));
         G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        configured = true;
+        configured.done();
     }
     const int grid = spa_grid(a.N, nlist);
     int rc = ws.ensure_spa((size_t)grid * a.N, stream);

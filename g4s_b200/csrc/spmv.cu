@@ -637,10 +637,12 @@ __global__ void localize_list_kernel(const int *__restrict__ flags, const int *_
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < cols && flags[c]) needed[pos[c]] = c;
 }
-__global__ void localize_rewrite_kernel(int *__restrict__ colids, long long nnz, int lo, int hi, const int *__restrict__ pos) {
+// writes the plan's PRIVATE localized copy; the handle's own column ids are never modified
+__global__ void localize_rewrite_kernel(const int *__restrict__ colids, int *__restrict__ out, long long nnz, int lo, int hi,
+                                        const int *__restrict__ pos) {
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
-        const int c = colids[k];
-        if (c < lo || c >= hi) colids[k] = -1 - pos[c];
+        const int c = __ldg(colids + k);
+        out[k] = (c < lo || c >= hi) ? -1 - __ldg(pos + c) : c;
     }
 }
 
@@ -698,8 +700,8 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     auto k0 = spmv_chunk_kernel<CAP, NBUF, WARPS, false, false>;
     auto k1 = spmv_chunk_kernel<CAP, NBUF, WARPS, true, false>;
     auto kp = spmv_chunk_kernel<CAP, NBUF, WARPS, false, true>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;  // keyed by the CTAs per SM: shapes that share an instantiation differ in the carve-out
+    if (configured.needs(ctas_per_sm)) {
         G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -708,7 +710,7 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
         G4S_CUDA(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         G4S_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        configured = true;
+        configured.done(ctas_per_sm);
     }
     long long want = ((long long)(args.nchunks - args.chunk_begin) + WARPS - 1) / WARPS;
     int grid = (int)std::min<long long>(want, (long long)sm_count() * ctas_per_sm);
@@ -852,6 +854,7 @@ void spmv_free_plan(g4s_csr *h) {
     if (p.part_needed) cudaFree(p.part_needed);
     if (p.part_halo) cudaFree(p.part_halo);
     if (p.part_halo_done) cudaFree(p.part_halo_done);
+    if (p.part_colids) cudaFree(p.part_colids);
     const int lanes = p.lanes_per_row, variant = p.variant;
     p = SpmvPlan();
     p.lanes_per_row = lanes;
@@ -861,8 +864,6 @@ void spmv_free_plan(g4s_csr *h) {
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
              const XParts *parts, int chunk_begin, int chunk_end) {
     if (h->rows == 0) return G4S_OK;
-    if (h->localized && !parts)
-        return fail(G4S_ERR_INVALID, "this handle's column ids were localized by a partitioned product; use g4s_spmv_partitioned_device");
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     const SpmvPlan &p = h->plan;
@@ -874,7 +875,9 @@ int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool ac
     }
     SpmvArgs a;
     a.rowptr = h->rowptr;
-    a.colids = h->colids;
+    // a partitioned product on a localized plan reads the plan's private copy of the column ids (remote columns
+    // numbered -1 - k); the handle's own array keeps the global ids for every other entry point
+    a.colids = (parts && parts->halo && h->plan.part_colids) ? h->plan.part_colids : h->colids;
     a.values = h->values;
     a.x = x;
     a.y = y;
@@ -942,10 +945,20 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     int rc = spmv_build_plan(h, stream);
     if (rc) return rc;
     SpmvPlan &p = h->plan;
-    if (h->localized && (p.part_lo != xp.lo || p.part_hi != xp.hi))
-        return fail(G4S_ERR_INVALID, "partitioned SpMV: the handle was localized for another column range");
-    if (!p.part_flags && h->owns && !h->localized && world > 1) {
-        // first partitioned product on an owned handle: number the remote columns and rewrite their ids (once)
+    if (p.part_colids && (p.part_lo != xp.lo || p.part_hi != xp.hi)) {  // another owned range: localize again
+        cudaFree(p.part_colids);
+        cudaFree(p.part_needed);
+        cudaFree(p.part_halo);
+        cudaFree(p.part_halo_done);
+        p.part_colids = nullptr;
+        p.part_needed = nullptr;
+        p.part_halo = nullptr;
+        p.part_halo_done = nullptr;
+    }
+    if (!p.part_colids && world > 1) {
+        // first partitioned product for this owned range: number the remote columns and write a private copy of the
+        // column ids in which they read -1 - k (once; the handle's own arrays are left untouched, so the handle
+        // stays valid for every other entry point and borrowed arrays are never modified)
         const int cols = h->cols, grid = sm_count() * 8;
         int *flags = nullptr, *pos = nullptr;
         G4S_CUDA(cudaMalloc(&flags, sizeof(int) * ((size_t)cols + 1)));
@@ -961,19 +974,19 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         G4S_CUDA(cudaMalloc(&p.part_needed, sizeof(int) * (size_t)std::max<long long>(nn, 1)));
         G4S_CUDA(cudaMalloc(&p.part_halo, sizeof(double) * (size_t)std::max<long long>(nn, 1)));
         G4S_CUDA(cudaMalloc(&p.part_halo_done, sizeof(unsigned long long)));
+        G4S_CUDA(cudaMalloc(&p.part_colids, sizeof(int) * (size_t)std::max<long long>(h->nnz, 1)));
         G4S_CUDA(cudaMemsetAsync(p.part_halo_done, 0, sizeof(unsigned long long), stream));
         if (cols) {
             localize_list_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(flags, pos, cols, p.part_needed);
             G4S_CHECK_LAUNCH("localize_list_kernel");
         }
         if (h->nnz) {
-            localize_rewrite_kernel<<<grid, 256, 0, stream>>>(h->colids, h->nnz, xp.lo, xp.hi, pos);
+            localize_rewrite_kernel<<<grid, 256, 0, stream>>>(h->colids, p.part_colids, h->nnz, xp.lo, xp.hi, pos);
             G4S_CHECK_LAUNCH("localize_rewrite_kernel");
         }
         G4S_CUDA(cudaStreamSynchronize(stream));
         cudaFree(flags);
         cudaFree(pos);
-        h->localized = true;
         p.part_products = 0;
         // which ranks own those columns: a product only has to wait for them (for a stencil: the two neighbours),
         // not for all ranks of the box
@@ -1005,7 +1018,7 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     xp.halo_target = 0;
     xp.gather_ctas = 0;
     xp.owner_mask = 0xffu;
-    if (h->localized) {
+    if (p.part_colids) {
         const long long want = ((long long)p.nchunks + 8) / 9;  // grid of the 1 x 9 x 2 shape (launch_chunk_kernel)
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 2));
         xp.needed = p.part_needed;

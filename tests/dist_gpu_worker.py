@@ -41,6 +41,13 @@ def main():
                     op.apply(xl, yl)
             torch.cuda.synchronize()
             if mode == "peer":
+                # the partitioned product works on a private copy of the column ids: the handle must still serve the
+                # plain entry points with its global ids (the first version rewrote them in place)
+                y2 = op.A.spmv(x)
+                good2 = bool(np.all(np.abs(y2 - want[op.c0:op.c1]) <= 1e-12 * scale[op.c0:op.c1] + 1e-300))
+                if not good2:
+                    print("rank %d: %s: handle unusable after a partitioned product" % (rank, name), flush=True)
+                ok = ok and good2
                 op.close()
             err = np.abs(yl.cpu().numpy() - want[op.c0:op.c1])
             good = bool(np.all(err <= 1e-12 * scale[op.c0:op.c1] + 1e-300))
