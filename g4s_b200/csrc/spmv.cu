@@ -306,6 +306,13 @@ struct XParts {
     unsigned long long halo_target;
     int gather_ctas;
     unsigned owner_mask;  // ranks whose flags this rank waits for (the owners of its remote columns; all if unknown)
+    // dynamic tail (localized plans): the last pool_n chunks of the sweep are not dealt out statically but claimed one at
+    // a time from pool_counter by whichever warp runs out of work first — the gather CTAs and the warps that had to wait
+    // for a peer start their matrix stream late, and with a purely static deal the whole launch ends that much later.
+    // The counter only grows: this launch's claims start at pool_base (every warp's last, failing claim is counted too).
+    unsigned long long *pool_counter;
+    unsigned long long pool_base;
+    int pool_n;
 };
 __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
     if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
@@ -370,8 +377,8 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
     const int g = lane / L, sub = lane % L;
     const double *__restrict__ x = a.x;
     if (PART && xp.halo) {
-        // Localized handle: remote entries carry column -1 - k and read halo[k], which the gather CTAs filled from the
-        // owners' memory earlier in this launch (ld.global.cg: the halo was written by other SMs during this kernel).
+        // Localized plan: remote entries carry column -1 - k and read halo[k], which the gather CTAs filled from the
+        // owners' memory earlier in this launch.
         const double *halo = xp.halo;
         for (int base = 0; base < nloc; base += PER_PASS) {
             const int r = base + g;
@@ -389,8 +396,15 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
             const int ke = e - a0;
 #pragma unroll 4
             for (; k < ke; k += L) {
+                // one load instruction for both kinds of entry (a pointer select, no divergent branch), cached in L1:
+                // this SM cannot hold a stale copy of a halo line, because it only reads the halo after the acquire on
+                // halo_done and L1 starts every launch empty.  (The first version chose between ld.global.nc and
+                // ld.global.cg per element: the boundary chunks ran ~4x slower than interior ones, which at 8 GPUs —
+                // 4 % of a rank's chunks — cost 12 % of the step.)
                 const int c = buf.cols[k];
-                const double xv = c >= 0 ? __ldg(x + c) : __ldcg(halo + (-1 - c));
+                const double *px = c >= 0 ? x + c : halo + (-1 - c);
+                double xv;
+                asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(xv) : "l"(px));
                 acc = fma(buf.vals[k], xv, acc);
             }
 #pragma unroll
@@ -487,14 +501,25 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
     // phases of the sweep, to de-synchronise the NVLink-bound chunks at the ends of a rank's range, was measured:
     // 8 bands cost more in x re-reads — 0.42 -> 0.52 ms on 8 M rows — than the de-synchronisation gains.)
     const int nit = wglobal < a.nchunks ? (int)(((long long)a.nchunks - wglobal + stride - 1) / stride) : 0;
-    // with an in-kernel halo every warp starts in the MIDDLE of its list and wraps around: the chunks that need the
-    // halo sit at the two ends of a rank's range, so they come up half a kernel after the gather CTAs started, and
-    // the whole grid still sweeps one band of rows at a time
-    const int rot = (PART && xp.halo) ? nit / 2 : 0;
-    auto chunk_at = [&](int i) -> long long {
-        int k = i + rot;
-        if (k >= nit) k -= nit;
-        return (long long)wglobal + (long long)k * stride;
+    // With an in-kernel halo the whole grid sweeps the chunk list ROTATED by half its length: the chunks that need the
+    // halo sit at the two ends of a rank's range, so they come up half a kernel after the gather CTAs started.  Position
+    // rho of the rotated sweep is chunk (rho + mid) mod n; positions below n_static are dealt out round-robin, the rest
+    // (the dynamic tail) is claimed from a counter.
+    const bool dyn = PART && NBUF == 1 && xp.halo != nullptr;
+    const int n_all = a.nchunks, mid = dyn ? n_all / 2 : 0;
+    const int n_static = dyn ? n_all - xp.pool_n : n_all;
+    auto chunk_of = [&](long long rho) -> long long {
+        long long c = rho + mid;
+        return c >= n_all ? c - n_all : c;
+    };
+    auto chunk_at = [&](int i) -> long long { return (long long)wglobal + (long long)i * stride; };
+    // lane 0: the position after rho (static successor, else one claim from the pool; -1: the sweep is over)
+    auto next_pos = [&](long long rho) -> long long {
+        long long nx = rho + stride;
+        if (rho < n_static && nx < n_static) return nx;
+        if (xp.pool_n <= 0 && n_static >= n_all) return -1;
+        const unsigned long long t = atomicAdd(xp.pool_counter, 1ULL) - xp.pool_base;
+        return (long long)t < (long long)xp.pool_n ? (long long)n_static + (long long)t : -1;
     };
     if (PART && xp.flags && xp.signal[0] && blockIdx.x == 0 && warp == 0 && lane < xp.world) {
         // publish this rank's slice for this product (it was written before the launch): a release store of the epoch
@@ -502,17 +527,27 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         __threadfence_system();
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xp.signal[lane] + xp.self), "l"(xp.epoch) : "memory");
     }
+    long long cur = -1;  // dyn: this warp's current position of the rotated sweep (warp-uniform)
     if (lane == 0) {
         policy = policy_evict_first();
         for (int b = 0; b < NBUF; ++b) mbar_init(&bar[b], 1);
         fence_mbar_init();
-        for (int b = 0; b < NBUF; ++b) {
-            if (b < nit) {
-                const long long c = chunk_at(b);
-                issue(b, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
+        if (dyn) {
+            cur = wglobal < n_static ? (long long)wglobal : next_pos((long long)n_static);
+            if (cur >= 0) {
+                const long long c = chunk_of(cur);
+                issue(0, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
+            }
+        } else {
+            for (int b = 0; b < NBUF; ++b) {
+                if (b < nit) {
+                    const long long c = chunk_at(b);
+                    issue(b, __ldg(a.desc + c).y, __ldg(a.desc + c + 1).y);
+                }
             }
         }
     }
+    if (dyn) cur = __shfl_sync(0xffffffffu, cur, 0);
     __syncwarp();
 
     bool peers_ready = !PART || xp.flags == nullptr;
@@ -538,8 +573,8 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
         __syncwarp();
         if (lane == 0) atomicAdd(xp.halo_done, 1ULL);
     }
-    for (int it = 0; it < nit; ++it) {
-        const long long c = chunk_at(it);
+    for (int it = 0; dyn ? cur >= 0 : it < nit; ++it) {
+        const long long c = dyn ? chunk_of(cur) : chunk_at(it);
         const int b = it % NBUF;
         const uint32_t parity = (it / NBUF) & 1;
         const int2 d0 = __ldg(a.desc + c), d1 = __ldg(a.desc + c + 1);
@@ -553,12 +588,19 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
             rp0 = __ldg(a.rowptr + d0.x + (lane >> lg));
             rp1 = __ldg(a.rowptr + d0.x + (lane >> lg) + 1);
         }
-        const bool has_next = it + NBUF < nit;
+        bool has_next = it + NBUF < nit;
+        long long nxt = -1;
         int2 n0 = make_int2(0, 0), n1 = n0;
-        if (lane == 0 && has_next) {
-            const long long next = chunk_at(it + NBUF);
-            n0 = __ldg(a.desc + next);
-            n1 = __ldg(a.desc + next + 1);
+        if (lane == 0) {
+            if (dyn) {
+                nxt = next_pos(cur);
+                has_next = nxt >= 0;
+            }
+            if (has_next) {
+                const long long next = dyn ? chunk_of(nxt) : chunk_at(it + NBUF);
+                n0 = __ldg(a.desc + next);
+                n1 = __ldg(a.desc + next + 1);
+            }
         }
         mbar_wait(&bar[b], parity);
         const ChunkBuf<CAP> &buf = bufs[b];
@@ -598,6 +640,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
 #undef G4S_CHUNK_CASE
         __syncwarp();  // every lane is done reading slot b
         if (lane == 0 && has_next) issue(b, n0.y, n1.y);
+        if (dyn) cur = __shfl_sync(0xffffffffu, nxt, 0);
     }
     // one warp per GPU always observes every rank's flag before the kernel ends, even when no chunk was remote:
     // a rank can then never run two products ahead of a peer that still reads its double-buffered slice
@@ -730,6 +773,9 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     none.halo_target = 0;
     none.gather_ctas = 0;
     none.owner_mask = 0xffu;
+    none.pool_counter = nullptr;
+    none.pool_base = 0;
+    none.pool_n = 0;
     if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
     else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
     else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
@@ -973,9 +1019,9 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         p.part_n_needed = (int)nn;
         G4S_CUDA(cudaMalloc(&p.part_needed, sizeof(int) * (size_t)std::max<long long>(nn, 1)));
         G4S_CUDA(cudaMalloc(&p.part_halo, sizeof(double) * (size_t)std::max<long long>(nn, 1)));
-        G4S_CUDA(cudaMalloc(&p.part_halo_done, sizeof(unsigned long long)));
+        G4S_CUDA(cudaMalloc(&p.part_halo_done, 2 * sizeof(unsigned long long)));  // [0] gather warps done, [1] tail-pool claims
         G4S_CUDA(cudaMalloc(&p.part_colids, sizeof(int) * (size_t)std::max<long long>(h->nnz, 1)));
-        G4S_CUDA(cudaMemsetAsync(p.part_halo_done, 0, sizeof(unsigned long long), stream));
+        G4S_CUDA(cudaMemsetAsync(p.part_halo_done, 0, 2 * sizeof(unsigned long long), stream));
         if (cols) {
             localize_list_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(flags, pos, cols, p.part_needed);
             G4S_CHECK_LAUNCH("localize_list_kernel");
@@ -1018,6 +1064,9 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     xp.halo_target = 0;
     xp.gather_ctas = 0;
     xp.owner_mask = 0xffu;
+    xp.pool_counter = nullptr;
+    xp.pool_base = 0;
+    xp.pool_n = 0;
     if (p.part_colids) {
         const long long want = ((long long)p.nchunks + 8) / 9;  // grid of the 1 x 9 x 2 shape (launch_chunk_kernel)
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 2));
@@ -1029,6 +1078,15 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
         xp.owner_mask = p.part_owner_mask;
         p.part_products += 1;  // the counter only grows: product n is complete at n * (gather warps)
         xp.halo_target = p.part_products * (unsigned long long)xp.gather_ctas * 9ULL;
+        // dynamic tail: 1/16 of the chunks (G4S_SPMV_POOL_SHIFT: another power-of-two share; 31 or more: none).  Every
+        // warp of the grid makes exactly one failing claim, so a launch advances the counter by pool_n + warps.
+        static const int shift = [] {
+            const char *e = getenv("G4S_SPMV_POOL_SHIFT");
+            return e ? atoi(e) : 4;
+        }();
+        xp.pool_n = shift >= 31 ? 0 : (p.nchunks >> shift);
+        xp.pool_counter = p.part_halo_done + 1;
+        xp.pool_base = (p.part_products - 1) * ((unsigned long long)xp.pool_n + (unsigned long long)grid * 9ULL);
     }
     // the plain path indexes x by global column id: rebase the own slice (never dereferenced outside [lo, hi))
     return spmv_run(h, x_parts[self] - xp.lo, y, nullptr, false, stream, &xp, 0, -1);
