@@ -107,30 +107,6 @@ __global__ void __launch_bounds__(256) bsr3_spmm64_fma_kernel(int mb, const int 
 // Multi-GPU form of the DFMA kernel (one NVSwitch box, <= 8 GPUs): the dense operand B is row-partitioned like the block
 // rows, every rank keeps its slice in CUDA-IPC-shared memory, and the kernel reads the rows of B that other GPUs own
 // straight over NVLink — no halo exchange, no replicated B.  base[q] points at block row cut[q] of B.
-struct BParts {
-    const double *base[8];
-    int cut[9];
-    int world;
-};
-__device__ __forceinline__ const double *b_part_row(const BParts &bp, int J) {
-    const double *b = bp.base[0];
-    int cut = bp.cut[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-        const bool ge = i < bp.world && J >= bp.cut[i];
-        b = ge ? bp.base[i] : b;
-        cut = ge ? bp.cut[i] : cut;
-    }
-    return b + (size_t)(J - cut) * 3 * 64;
-}
-// the same lookup for a block column that differs from lane to lane (K-packed kernels): count the cuts at or below J and
-// index the parameter block with the result (two constant-bank loads) instead of carrying a pointer through seven selects
-__device__ __forceinline__ const double *b_part_row_lane(const BParts &bp, int J) {
-    int owner = 0;
-#pragma unroll
-    for (int i = 1; i < 8; ++i) owner += (i < bp.world && J >= bp.cut[i]) ? 1 : 0;
-    return bp.base[owner] + (size_t)(J - bp.cut[owner]) * 3 * 64;
-}
 __global__ void __launch_bounds__(256) bsr3_spmm64_fma_parts_kernel(int mb, const int *__restrict__ browptr,
                                                                     const int *__restrict__ bcolids,
                                                                     const double *__restrict__ bvalues,

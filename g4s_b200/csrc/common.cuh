@@ -120,6 +120,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -139,6 +142,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 // global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16, completes on `bar`.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
                                          uint64_t policy) {
@@ -150,5 +158,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 __device__ __forceinline__ double ldg_f64(const double *p) { return __ldg(p); }
+
+// ---- dense operand of the multi-GPU BSR SpMM: row-partitioned, every part in CUDA-IPC-shared memory ------------
+struct BParts {
+    const double *base[8];
+    int cut[9];
+    int world;
+};
+__device__ __forceinline__ const double *b_part_row(const BParts &bp, int J) {
+    const double *b = bp.base[0];
+    int cut = bp.cut[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        const bool ge = i < bp.world && J >= bp.cut[i];
+        b = ge ? bp.base[i] : b;
+        cut = ge ? bp.cut[i] : cut;
+    }
+    return b + (size_t)(J - cut) * 3 * 64;
+}
+// the same lookup for a block column that differs from lane to lane (K-packed kernels): count the cuts at or below J and
+// index the parameter block with the result (two constant-bank loads) instead of carrying a pointer through seven selects
+__device__ __forceinline__ const double *b_part_row_lane(const BParts &bp, int J) {
+    int owner = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) owner += (i < bp.world && J >= bp.cut[i]) ? 1 : 0;
+    return bp.base[owner] + (size_t)(J - bp.cut[owner]) * 3 * 64;
+}
 
 }  // namespace g4s

@@ -291,6 +291,44 @@ int g4s_bsr3_spmm64_partitioned_device(int mb_local, const int *browptr_dev, con
                                        const double *bvalues_dev, int world, const double *const *B_parts,
                                        const int *cuts, double *C_dev, void *stream);
 
+/* Inspector / executor form for bs = 3, ncol = 64 (the role of MKL's mkl_sparse_set_mm_hint + mkl_sparse_optimize):
+ * a sliding-window sweep (csrc/bsr_sweep.cu).  The block rows are handed over as STRIPS — lists of block rows that one
+ * lane group sweeps in order while it keeps three consecutive rows of the strip in registers, so that a row of B
+ * is loaded once for all rows of the window that reference it.  Good strips are grid lines of a mesh
+ * (g4s_grid_pencil_strips) or, for any banded matrix in its natural order, runs of consecutive rows (nstrips = 0:
+ * runs of 64).  16 consecutive strips form the tile of one CTA and should be neighbours in the mesh.
+ *   create      : browptr_dev / bcolids_dev are DEVICE arrays (as everywhere in this section); strip_ptr[nstrips+1] and
+ *                 strip_rows[mb] are HOST arrays and must cover every block row exactly once.  world > 1: this rank's
+ *                 rows with GLOBAL block-column ids, B row-partitioned by cuts[world+1] (see
+ *                 g4s_bsr3_spmm64_partitioned_device).  Builds the schedule on the host (OpenMP) and allocates the plan
+ *                 stream on the device (about 81 bytes per block).
+ *   set_values  : (re)packs the 3x3 blocks into the plan stream; call after create and whenever the values change.
+ *   spmm64      : C = A B.  B must be finite: blocks absent from a step are stored as explicit zeros.
+ *   info        : slot_fill = blocks / block slots moved (1.0: every loaded row of B feeds three blocks; a plan with a
+ *                 low fill is slower than g4s_bsr_spmm_device and should not be used). */
+typedef struct g4s_bsr_plan *g4s_bsr_plan_t;
+int g4s_bsr3_plan_create(g4s_bsr_plan_t *out, int mb, int kb, const int *browptr_dev, const int *bcolids_dev, int nstrips,
+                         const int *strip_ptr, const int *strip_rows, int world, const int *cuts);
+int g4s_bsr3_plan_set_values(g4s_bsr_plan_t plan, const double *bvalues_dev, void *stream);
+int g4s_bsr3_plan_spmm64_device(g4s_bsr_plan_t plan, const double *B_dev, double *C_dev, void *stream);
+int g4s_bsr3_plan_spmm64_partitioned_device(g4s_bsr_plan_t plan, int world, const double *const *B_parts, const int *cuts,
+                                            double *C_dev, void *stream);
+int g4s_bsr3_plan_info(g4s_bsr_plan_t plan, double *slot_fill, long long *stream_bytes, int *nstages, int *ntiles,
+                       int *stage_smem_bytes);
+int g4s_bsr3_plan_destroy(g4s_bsr_plan_t plan);
+/* The schedule alone, built from HOST arrays without touching a device (what the CPU tests replay): per stage the
+ * table entry (byte offset in the plan stream, chunk bytes | expected bytes << 32), per tile its first stage, the
+ * concatenated stage headers + position lists (`meta`, stage q at meta_off[q]), and per block the index (in doubles) of its
+ * slot in the plan stream.  Output arrays are malloc'd (g4s_free); any of the pointers may be null. */
+int g4s_bsr3_plan_inspect_host(int mb, int kb, const int *browptr, const int *bcolids, int nstrips, const int *strip_ptr,
+                               const int *strip_rows, int world, const int *cuts, int *nstages, int *ntiles,
+                               long long *stream_bytes, int *stage_smem_bytes, double *slot_fill, long long **stage_table,
+                               int **tile_ptr, int **meta, long long **meta_off, long long **base);
+/* Strips for the nodes k_begin <= k < k_end of an n0 x n1 x n2 grid numbered n0 fastest, as LOCAL row numbers
+ * ((k - k_begin)*n1 + j)*n0 + i: one strip per grid line along the third axis, the lines of a p0 x p1 patch consecutive
+ * (p0 = p1 = 4: one patch per tile).  strip_ptr (host) receives n0*n1 + 1 offsets, strip_rows n0*n1*(k_end-k_begin) rows. */
+int g4s_grid_pencil_strips(int n0, int n1, int k_begin, int k_end, int p0, int p1, int *strip_ptr, int *strip_rows);
+
 /* ------------------------------------------------------------------------------------------------------
  * The G4S graph engine ABI.  `spmm_dense` is the engine CitcomS calls through E->spmm_dense
  * (citcoms/bin/Citcom.c:45-48,93; citcoms/lib/global_defs.h:48-49,854-857); the reference declares it but does not

@@ -342,3 +342,18 @@ def test_dev_size_config5_bsr_closed_form(g4s):
                                            C.c_void_p(0)))
     torch.cuda.synchronize()
     assert torch.equal(C1, C2)
+    # the sliding-window sweep (inspector / executor) on the same matrix: grid lines along the third axis, 4 x 4 patches
+    from g4s_b200 import bsr
+
+    plan = bsr.BsrPlan(mb, mb, rp, ci, bsr.grid_pencil_strips(n, n, 0, n)).set_values(blocks.data_ptr())
+    info = plan.info()
+    assert info["slot_fill"] > 0.95, info
+    plan.spmm(B.data_ptr(), C2.data_ptr())
+    torch.cuda.synchronize()
+    # same products in another order: |C| <= 52.3 * 3 here, each of the 81 terms rounds once
+    assert float((C1 - C2).abs().max()) <= 1e-12 * 81 * 3
+    B.fill_(1.0)
+    plan.spmm(B.data_ptr(), C2.data_ptr())
+    torch.cuda.synchronize()
+    assert float((C2 - want).abs().max()) <= 1e-12 * (29.0 + 1.3 * 26)
+    plan.destroy()
