@@ -260,6 +260,8 @@ def per_step_times(torch, dist, step, steps, barrier):
 
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world):
+    if "LOCAL_RANK" in os.environ:  # torchrun exports OMP_NUM_THREADS=1: give the host-side inspectors their share of the cores
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // max(world, 1)))
     import torch
 
     import g4s_b200
@@ -421,6 +423,20 @@ def run_ours(args, rank, world):
     spgemm_multi = None
     if dist is not None and not args.no_spgemm:
         spgemm_multi = bench_spgemm_dist(g4s_b200, torch, dist, args, rank, world)
+    bsr_line = None
+    if not args.no_bsr:
+        if world > 1:  # free the SpMV operator first: the BSR rider needs ~20 GB per GPU
+            op.close()
+            if hasattr(op, "A"):
+                op.A.make_empty()
+        else:
+            A.make_empty()
+        del x, y
+        torch.cuda.empty_cache()
+        try:
+            bsr_line = bench_bsr(g4s_b200, torch, dist, rank, world, measured_peak()[0])
+        except Exception as e:  # the headline line must not depend on a rider (collectives inside: all ranks fail alike)
+            bsr_line = {"error": str(e)[:300]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -461,6 +477,8 @@ def run_ours(args, rank, world):
     }
     if spgemm_multi is not None:
         line["spgemm"] = spgemm_multi
+    if bsr_line is not None:
+        line["bsr_spmm"] = bsr_line
     if world == 1 and not args.no_cpu:
         from oracle.binding import Oracle, Ref
 
@@ -488,9 +506,9 @@ def run_ours(args, rank, world):
 
 
 def bench_other_configs(g4s_b200, torch, peak):
-    """The remaining BASELINE configs on one GPU, device-timed (CUDA events, 3 warm-ups, 20 / 5 launches): configs[0]
-    (2-D 5-point SpMV, L2-resident), configs[2] (R-MAT scale 24 SpMV) and configs[4] at its development size (BSR 3x3 SpMM x 64
-    columns on a 128^3-node mesh; 256^3 is the 8-GPU size).  `frac` = algorithmic bytes / time over the measured HBM peak."""
+    """BASELINE configs[0] (2-D 5-point SpMV, L2-resident) and configs[2] (R-MAT scale 24 SpMV) on one GPU, device-timed
+    (CUDA events, 3 warm-ups, 20 launches).  `frac` = algorithmic bytes / time over the measured HBM peak.  configs[4] has
+    its own rider, bench_bsr()."""
     import ctypes as C
 
     import numpy as np
@@ -525,35 +543,160 @@ def bench_other_configs(g4s_b200, torch, peak):
                     "frac_of_hbm_peak": nbytes / ms / 1e6 / peak, "note": note}
         A.make_empty()
         del x, y
-    n, ncol = 128, 64
-    P = g4s_b200.CSR.laplacian3d27(n)
+    return out
+
+
+BSR_GRID = {1: 128, 2: 161, 4: 203, 8: 256}   # configs[4]: 256^3 nodes on 8 GPUs; n^3 ~ 128^3 * N below (weak scaling)
+
+
+def det_b_torch(torch, row0, row1, device):
+    """Rows [row0, row1) of the dense operand, B[i, c] = det_x(64 i + c): regenerable anywhere."""
+    return det_x_torch(torch, row0 * 64, row1 * 64, device)
+
+
+def bench_bsr(g4s_b200, torch, dist, rank, world, peak, steps=10):
+    """BASELINE configs[4]: C = A B, A = 3x3-block 27-point mesh operator (diagonal block 26 I + J, off-diagonal -I - 0.1 J;
+    SURVEY.md §8d), B 64 dense columns, through the sliding-window sweep plan (g4s_bsr3_plan_*).  N GPUs: the n^3-node mesh
+    (n = BSR_GRID[N]; 256^3 at N = 8) is cut into slabs of planes, every rank keeps its rows of B in CUDA-IPC memory and the
+    stage loader's TMA copies read the two halo planes straight from the neighbours over NVLink; one 4-byte all-reduce per
+    step orders the product after the peers' writes to B.  Device-timed, max over ranks; parity inside: B = 1 gives
+    29 - 1.3 (#neighbours) in every entry (closed form, all rows), and stretches of rows at both ends and inside the slab
+    are checked against the oracle's BSR product on rows regenerated on the CPU (tolerance 1e-12 |A||B|)."""
+    import ctypes as C
+
+    from g4s_b200 import bsr
+    from g4s_b200._lib import check
+    from g4s_b200.dist import DistBsrSpMM, _DevArray
+    from oracle.binding import Oracle
+
+    L = g4s_b200.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = BSR_GRID.get(world, int(round((128 ** 3 * world) ** (1.0 / 3.0))))
+    plane = n * n
+    kcut = [(n * q) // world for q in range(world + 1)]
+    cuts = [k * plane for k in kcut]
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    P = g4s_b200.CSR.laplacian3d27(n, r0, r1)
     rp, ci, va = P.device_arrays()
     nb, mb = P.nnz, P.rows
-    vals = torch.as_tensor(_DevArray(va, nb, "<f8"), device="cuda")
-    J = torch.ones(3, 3, dtype=torch.float64, device="cuda")
-    I3 = torch.eye(3, dtype=torch.float64, device="cuda")
+    vals = torch.as_tensor(_DevArray(va, nb, "<f8"), device=dev)
+    J = torch.ones(3, 3, dtype=torch.float64, device=dev)
+    I3 = torch.eye(3, dtype=torch.float64, device=dev)
     diag = (vals > 0).double()[:, None, None]
     blocks = (diag * (26 * I3 + J) + (1 - diag) * (-I3 - 0.1 * J)).contiguous().reshape(-1)
-    del diag
-    g = torch.Generator(device="cuda").manual_seed(777)
-    B = torch.rand(mb * 3 * ncol, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
-    Cd = torch.empty(mb * 3 * ncol, dtype=torch.float64, device="cuda")
-    order = np.empty(mb, dtype=np.int32)
-    check(L.g4s_grid_pencil_order(C.c_int(n), C.c_int(n), C.c_int(n), C.c_int(4), C.c_int(4),
-                                  order.ctypes.data_as(C.c_void_p), None, None))
-    od = torch.from_numpy(order).cuda()
-    nbytes = 76.0 * nb + 4 * (mb + 1) + 2 * 8.0 * 3 * mb * ncol
-    flops = 2.0 * 9 * nb * ncol
-    plain = timeit(lambda: check(L.g4s_bsr_spmm_device(
-        C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci), C.c_void_p(blocks.data_ptr()), C.c_int(ncol),
-        C.c_void_p(B.data_ptr()), C.c_void_p(Cd.data_ptr()), C.c_void_p(0))), 5)
-    tiled = timeit(lambda: check(L.g4s_bsr3_spmm64_ordered_device(
-        C.c_int(mb), C.c_int(mb), C.c_void_p(rp), C.c_void_p(ci), C.c_void_p(blocks.data_ptr()), C.c_void_p(B.data_ptr()),
-        C.c_void_p(Cd.data_ptr()), C.c_void_p(od.data_ptr()), C.c_void_p(0), C.c_int(0), C.c_void_p(0))), 5)
-    for name, ms in (("natural row order", plain), ("tile-major (4x4 pencil) row order", tiled)):
-        out["configs[4] bsr 3x3 spmm x 64 cols, 128^3 nodes, " + name] = {
-            "blocks": nb, "ms": ms, "algorithmic_gbs": nbytes / ms / 1e6, "tflops": flops / ms / 1e9,
-            "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+    del diag, vals
+    strips = bsr.grid_pencil_strips(n, n, kcut[rank], kcut[rank + 1])
+    Cd = torch.empty(mb * 192, dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    if world == 1:
+        plan = bsr.BsrPlan(mb, mb, rp, ci, strips).set_values(blocks.data_ptr())
+        Bd = torch.empty(mb * 192, dtype=torch.float64, device=dev)
+        info = plan.info()
+
+        def step():
+            plan.spmm(Bd.data_ptr(), Cd.data_ptr())
+    else:
+        op = DistBsrSpMM(torch.as_tensor(_DevArray(rp, mb + 1, "<i4"), device=dev), torch.as_tensor(_DevArray(ci, nb, "<i4"), device=dev),
+                         blocks, cuts, strips=strips)
+        Bd = op.B_local.view(-1)
+        info = op.plan.info()
+
+        def step():
+            op.apply(Cd.view(mb * 3, 64))
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def set_b(t):
+        if world > 1:
+            op.begin_update()
+        Bd.copy_(t)
+
+    set_b(det_b_torch(torch, r0 * 3, r1 * 3, dev))
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    # ---- parity ----------------------------------------------------------------------------------------------------------
+    oracle = Oracle()
+    got_all = Cd.view(mb * 3, 64)
+    stretch, worst, checked = 512, 0.0, 0
+    for s0 in sorted(set(int(v) for v in np.linspace(r0, max(r0, r1 - stretch), 5))):
+        s1 = min(s0 + stretch, r1)
+        A = oracle.gen_laplacian3d27(n, s0, s1)
+        lo, hi = int(A[3].min()), int(A[3].max()) + 1
+        hb = np.where(A[4] > 0, 1.0, 0.0)[:, None, None]
+        hblocks = hb * (26 * np.eye(3) + np.ones((3, 3))) + (1 - hb) * (-np.eye(3) - 0.1 * np.ones((3, 3)))
+        Bw = det_x_numpy(np.arange(lo * 192, hi * 192, dtype=np.int64)).reshape((hi - lo) * 3, 64)
+        col = (A[3] - lo).astype(np.int32)
+        want = oracle.bsr_spmm(A[2], col, hblocks.reshape(-1), 3, Bw)
+        absw = oracle.bsr_spmm(A[2], col, np.abs(hblocks).reshape(-1), 3, np.abs(Bw))
+        got = got_all[(s0 - r0) * 3:(s1 - r0) * 3].cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(absw, 1e-300))))
+        checked += s1 - s0
+    set_b(torch.ones(mb * 192, dtype=torch.float64, device=dev))
+    step()
+    torch.cuda.synchronize()
+    r = torch.arange(r0, r1, dtype=torch.int64, device=dev)
+    cnt = torch.ones(mb, dtype=torch.float64, device=dev)
+    for q in (r % n, (r // n) % n, r // plane):
+        cnt *= 3.0 - ((q == 0) | (q == n - 1)).double()
+    want1 = 29.0 - 1.3 * (cnt - 1.0)
+    bad = int(((got_all - want1[:, None].repeat_interleave(3, dim=0)).abs().amax(dim=1) > 1e-12 * (29.0 + 1.3 * 26)).sum().item())
+    del r, cnt, want1
+    bytes_local = 76.0 * nb + 4.0 * (mb + 1) + 2 * 8.0 * 192 * mb
+    t = torch.tensor([ms, bytes_local, 18.0 * nb * 64, float(bad), float(checked), float(mb)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    w = torch.tensor([worst], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    ms_max, tot_bytes, tot_flops = float(tmax[0].item()), float(t[1].item()), float(t[2].item())
+    bad, checked, rows_all, worst = int(t[3].item()), int(t[4].item()), int(t[5].item()), float(w.item())
+    out = {"metric": "bsr_spmm_algorithmic_gbs", "value": tot_bytes / ms_max / 1e6, "unit": "GB/s", "ms": ms_max, "n_gpus": world,
+           "tflops_fp64": tot_flops / ms_max / 1e9, "steps": steps,
+           "config": {"workload": "BSR 3x3 SpMM x 64 columns, 27-block mesh operator on %d^3 nodes (BASELINE configs[4]%s)"
+                                  % (n, "" if n == 256 else "; 256^3 is the 8-GPU size, n^3 ~ 128^3 N below"),
+                      "block_rows": rows_all, "bytes": tot_bytes, "flops": tot_flops,
+                      "partition": "slabs of planes; rows of B in CUDA-IPC memory, halo planes read over NVLink by the stage "
+                                   "loader's TMA copies; one 4-byte all-reduce per step" if world > 1 else "1 GPU"},
+           "plan": dict(info, setup_seconds=setup_s),
+           "roofline": {"bound": "hbm", "kernel": "bsr3_sweep_kernel", "achieved": bytes_local / ms / 1e6 if world == 1
+                        else tot_bytes / world / ms_max / 1e6, "peak": peak, "unit": "GB/s",
+                        "frac": (tot_bytes / world / ms_max / 1e6) / peak,
+                        "note": "fp64 FMA-bound at this size as much as HBM-bound: 64.2 GFLOP per 10.7 GB; a warp issues one "
+                                "DFMA per 2.5-2.6 cycles per scheduler at best on this part (tools/micro/dfma_rate.cu)"},
+           "parity_check": {"ok": bad == 0 and worst <= 1e-12,
+                            "ones_closed_form": {"block_rows": rows_all, "mismatches": bad},
+                            "sampled_vs_oracle": {"block_rows": checked, "max_err_over_abs": worst, "tolerance": 1e-12}}}
+    if world == 1:  # the row-wise kernel of round 1 beside it
+        for _ in range(2):
+            check(L.g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci),
+                                        C.c_void_p(blocks.data_ptr()), C.c_int(64), C.c_void_p(Bd.data_ptr()),
+                                        C.c_void_p(Cd.data_ptr()), C.c_void_p(0)))
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            check(L.g4s_bsr_spmm_device(C.c_int(mb), C.c_int(mb), C.c_int(3), C.c_void_p(rp), C.c_void_p(ci),
+                                        C.c_void_p(blocks.data_ptr()), C.c_int(64), C.c_void_p(Bd.data_ptr()),
+                                        C.c_void_p(Cd.data_ptr()), C.c_void_p(0)))
+        e1.record()
+        torch.cuda.synchronize()
+        out["rowwise_kpack_kernel_ms"] = e0.elapsed_time(e1) / 5
+        plan.destroy()
+    else:
+        op.close()
     P.make_empty()
     return out
 
@@ -674,7 +817,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity check of the timed operator")
     ap.add_argument("--no-spgemm", action="store_true")
-    ap.add_argument("--no-other", action="store_true", help="skip the single-GPU riders for configs[0], [2], [4]")
+    ap.add_argument("--no-other", action="store_true", help="skip the single-GPU riders for configs[0], [2]")
+    ap.add_argument("--no-bsr", action="store_true", help="skip the configs[4] rider (BSR SpMM)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -71,7 +71,7 @@ class BsrPlan:
             pass
 
 
-def inspect_host(mb, kb, browptr, bcolids, strips=None, world=1, cuts=None):
+def inspect_host(mb, kb, browptr, bcolids, strips=None, world=1, cuts=None, grid=296, ctas_per_sm=2):
     """The schedule alone from host arrays (g4s_bsr3_plan_inspect_host): no device is touched."""
     L = lib()
     rp = np.ascontiguousarray(browptr, dtype=np.int32)
@@ -85,12 +85,13 @@ def inspect_host(mb, kb, browptr, bcolids, strips=None, world=1, cuts=None):
     cc = (C.c_int * (world + 1))(*[int(c) for c in cuts]) if cuts is not None else None
     ns, nt, sb, sm, fill = C.c_int(), C.c_int(), C.c_longlong(), C.c_int(), C.c_double()
     i64p = C.POINTER(C.c_longlong)
-    st, tp, meta, moff, base = i64p(), i32p(), i32p(), i64p(), i64p()
+    st, tp, prod, meta, moff, base = i64p(), i32p(), i32p(), i32p(), i64p(), i64p()
     check(L.g4s_bsr3_plan_inspect_host(C.c_int(mb), C.c_int(kb), rp.ctypes.data_as(i32p), ci.ctypes.data_as(i32p), C.c_int(n),
                                        sp.ctypes.data_as(i32p) if sp is not None else None,
                                        sr.ctypes.data_as(i32p) if sr is not None else None, C.c_int(world), cc,
+                                       C.c_int(grid), C.c_int(ctas_per_sm),
                                        C.byref(ns), C.byref(nt), C.byref(sb), C.byref(sm), C.byref(fill), C.byref(st),
-                                       C.byref(tp), C.byref(meta), C.byref(moff), C.byref(base)))
+                                       C.byref(tp), C.byref(prod), C.byref(meta), C.byref(moff), C.byref(base)))
 
     def take(ptr, count, dtype):
         out = np.ctypeslib.as_array(ptr, shape=(max(count, 1),))[:count].astype(dtype, copy=True)
@@ -101,5 +102,6 @@ def inspect_host(mb, kb, browptr, bcolids, strips=None, world=1, cuts=None):
     moff_a = take(moff, nstages + 1, np.int64)
     return {"nstages": nstages, "ntiles": nt.value, "stream_bytes": sb.value, "stage_smem_bytes": sm.value,
             "slot_fill": fill.value, "stage_table": take(st, 2 * nstages, np.int64).reshape(nstages, 2),
-            "tile_ptr": take(tp, nt.value + 1, np.int32), "meta": take(meta, int(moff_a[-1]), np.int32),
+            "cta_ptr": take(tp, grid + 1, np.int32), "prod": take(prod, 64 * nstages, np.int32).reshape(nstages, 64),
+            "grid": grid, "ctas_per_sm": ctas_per_sm, "meta": take(meta, int(moff_a[-1]), np.int32),
             "meta_off": moff_a, "base": take(base, nb, np.int64)}

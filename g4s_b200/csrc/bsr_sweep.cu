@@ -19,8 +19,16 @@
 //     one contiguous chunk of the plan stream, so the block values are read from DRAM strictly sequentially;
 //   * a producer warp streams stages with the TMA engine (cp.async.bulk, SASS UBLKCP): one bulk copy for the chunk
 //     (L2 evict_first) and one per run of consecutive rows of B in the stage's union list (1536 B per row; for mesh
-//     operators a run is a 9 KB line of 6 nodes), double-buffered on full/empty mbarriers; consumers never touch global
-//     memory except to store finished rows of C.
+//     operators a run is a 9 KB line of 6 nodes), double-buffered on full/empty mbarriers; its copy descriptors are one
+//     coalesced int2 per lane from the plan's table, fetched a stage early.  The consumers never touch global memory
+//     except to store finished rows of C.
+//   * the plan fixes the grid (one CTA per SM of the device it was made on) and stores every CTA's stages consecutively,
+//     tiles dealt round-robin so that neighbouring patches are swept at the same time and share their halo rows of B
+//     through L2 (ncu: DRAM traffic 1.08x the algorithmic bytes).
+//   Measured alternatives (profiles/r02_bsr_sweep_summary.md): two 4-warp CTAs per SM with the loader folded into warp 0
+//   need stages of a third of a phase to fit shared memory and lose more to per-stage overhead and shallow prefetch
+//   (3.6-4.6 ms) than two warps per scheduler gain; a single warp per scheduler already issues a DFMA every 2.64 cycles
+//   against 2.46 with two (tools/micro/dfma_rate.cu), i.e. the FP64 pipe of this part tops out near 30 TFLOP/s.
 //
 // Per block the data path now carries 4 (B) + 5 (values, 8-lane broadcast) cycles against 9 cycles of DFMA.
 // Arithmetic: plain FP64 FMAs in a fixed, schedule-defined order (deterministic; differs from the row-order sum of the
@@ -58,9 +66,9 @@ struct SweepStage {
 
 struct SweepArgs {
     const unsigned char *stream;
-    const SweepStage *stages;
-    const int *tile_ptr;  // stages of tile t: [tile_ptr[t], tile_ptr[t+1])
-    int ntiles;
+    const int2 *prod;     // per stage 32 entries: lane i < 30: run i (first block column, length | first staged row << 8);
+                          // lane 30: byte offset of the chunk (lo, hi); lane 31: (chunk bytes, bytes the mbarrier expects)
+    const int *cta_ptr;   // stages of CTA b: [cta_ptr[b], cta_ptr[b+1])
     int stage_smem;       // bytes of one stage buffer (two are allocated)
 };
 
@@ -74,6 +82,76 @@ __device__ __forceinline__ void sweep_flush(double2 (&acc)[3][4], int row, doubl
     }
 }
 
+// warp 0: start the copies of one stage into `buf` (pd = this lane's entry of the stage's descriptor row)
+template <bool PARTS>
+__device__ __forceinline__ void sweep_issue(unsigned char *buf, uint64_t *full, const int2 pd, const SweepArgs &a,
+                                            const double *__restrict__ B, const BParts &bp, int lane) {
+    const int chunk_bytes = __shfl_sync(0xffffffffu, pd.x, 31), tx_bytes = __shfl_sync(0xffffffffu, pd.y, 31);
+    const unsigned off_lo = (unsigned)__shfl_sync(0xffffffffu, pd.x, 30), off_hi = (unsigned)__shfl_sync(0xffffffffu, pd.y, 30);
+    if (lane == 0) {
+        const unsigned long long off = ((unsigned long long)off_hi << 32) | off_lo;
+        mbar_arrive_expect_tx(full, (uint32_t)tx_bytes);
+        bulk_g2s(buf, a.stream + off, (uint32_t)chunk_bytes, full, policy_evict_first());
+    }
+    __syncwarp();
+    const int len = lane < 30 ? (pd.y & 0xff) : 0;
+    if (len > 0) {
+        const int J0 = pd.x, pre = pd.y >> 8;
+        const double *src = PARTS ? b_part_row_lane(bp, J0) : B + (size_t)J0 * SW_NODE;
+        bulk_g2s(buf + ((chunk_bytes + 127) & ~127) + (size_t)pre * (SW_NODE * 8), src, (uint32_t)len * (SW_NODE * 8), full,
+                 policy_evict_last());
+    }
+}
+
+// one stage by one consumer warp; ROT = how often the window has slid so far (mod 3): relative slot f of the records lives
+// in accumulator set (f + ROT) % 3, so sliding the window renames register sets at compile time instead of moving 48
+// register pairs (ncu: the moves were 7 % of the consumers' issue slots)
+template <int ROT>
+__device__ __forceinline__ void sweep_stage(double2 (&acc)[3][3][4], const unsigned char *sb, int strip, int l,
+                                            double *__restrict__ C) {
+    const int *hdr = reinterpret_cast<const int *>(sb);
+    const int S = hdr[1], rotate = hdr[2], b_off = hdr[3];
+    const int Spad = (S + 3) & ~3;
+    const int *ul = reinterpret_cast<const int *>(sb + SW_HDR_INTS * 4) + strip * Spad;
+    const double *rec = reinterpret_cast<const double *>(sb + SW_HDR_INTS * 4 + SW_STRIPS * 4 * Spad) + (size_t)strip * S * SW_REC;
+    const double *bb = reinterpret_cast<const double *>(sb + b_off) + 2 * l;
+    int u = S > 0 ? ul[0] : 0;
+    for (int t = 0; t < S; ++t) {
+        const double *br = bb + u * SW_NODE;
+        if (t + 1 < S) u = ul[t + 1];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            double av[10];
+#pragma unroll
+            for (int h = 0; h < 5; ++h) {
+                const double2 v = *reinterpret_cast<const double2 *>(rec + s * 10 + 2 * h);
+                av[2 * h] = v.x;
+                av[2 * h + 1] = v.y;
+            }
+            double2 bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bv[i] = *reinterpret_cast<const double2 *>(br + s * 64 + 16 * i);
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[(f + ROT) % 3][r][i].x = fma(av[f * 3 + r], bv[i].x, acc[(f + ROT) % 3][r][i].x);
+                        acc[(f + ROT) % 3][r][i].y = fma(av[f * 3 + r], bv[i].y, acc[(f + ROT) % 3][r][i].y);
+                    }
+        }
+        rec += SW_REC;
+    }
+    if (rotate) {  // end of a phase: the oldest row of the window is complete — store it; its set becomes the newest slot
+        sweep_flush(acc[ROT % 3], hdr[SW_HDR_ROWS + strip], C, l);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[ROT % 3][r][i] = make_double2(0.0, 0.0);
+    }
+}
+
 template <bool PARTS>
 __global__ void __launch_bounds__((SW_WARPS + 1) * 32, 1)
     bsr3_sweep_kernel(const SweepArgs a, const double *__restrict__ B, const __grid_constant__ BParts bp,
@@ -81,6 +159,7 @@ __global__ void __launch_bounds__((SW_WARPS + 1) * 32, 1)
     extern __shared__ __align__(128) unsigned char sw_smem[];
     __shared__ uint64_t bar_full[2], bar_empty[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = __ldg(a.cta_ptr + blockIdx.x), q1 = __ldg(a.cta_ptr + blockIdx.x + 1);
     if (threadIdx.x == 0) {
         mbar_init(&bar_full[0], 1);
         mbar_init(&bar_full[1], 1);
@@ -90,47 +169,19 @@ __global__ void __launch_bounds__((SW_WARPS + 1) * 32, 1)
     }
     __syncthreads();
     if (warp == SW_WARPS) {
-        // ---- producer: stage q of this CTA's tiles into buffer (it & 1) --------------------------------------------
-        const uint64_t pol_stream = policy_evict_first(), pol_b = policy_evict_last();
-        unsigned it = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            const int q0 = __ldg(a.tile_ptr + tile), q1 = __ldg(a.tile_ptr + tile + 1);
-            for (int q = q0; q < q1; ++q, ++it) {
-                const int st = it & 1;
-                unsigned char *buf = sw_smem + (size_t)st * a.stage_smem;
-                const longlong2 sd = __ldg(reinterpret_cast<const longlong2 *>(a.stages + q));
-                const long long off = sd.x;
-                const int chunk_bytes = (int)(sd.y & 0xffffffffLL), tx_bytes = (int)(sd.y >> 32);
-                const int *hdr = reinterpret_cast<const int *>(a.stream + off);
-                const int n_runs = __ldg(hdr), b_off = __ldg(hdr + 3);
-                int J0 = 0, len = 0;
-                if (lane < n_runs) {
-                    J0 = __ldg(hdr + SW_HDR_RUNS + 2 * lane);
-                    len = __ldg(hdr + SW_HDR_RUNS + 2 * lane + 1);
-                }
-                int pre = len;  // inclusive scan of the run lengths: where run `lane` starts in the staged list
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, pre, o);
-                    if (lane >= o) pre += t;
-                }
-                pre -= len;
-                if (it >= 2) mbar_wait(&bar_empty[st], ((it >> 1) - 1) & 1);  // the consumers are done with this buffer
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&bar_full[st], (uint32_t)tx_bytes);
-                    bulk_g2s(buf, a.stream + off, (uint32_t)chunk_bytes, &bar_full[st], pol_stream);
-                }
-                __syncwarp();
-                if (len > 0) {
-                    const double *src = PARTS ? b_part_row_lane(bp, J0) : B + (size_t)J0 * SW_NODE;
-                    bulk_g2s(buf + b_off + (size_t)pre * (SW_NODE * 8), src, (uint32_t)len * (SW_NODE * 8), &bar_full[st],
-                             pol_b);
-                }
-            }
+        // ---- producer: stage q into buffer (q - q0) & 1 as soon as the consumers have released it ------------------------
+        int2 pd = q0 < q1 ? __ldg(a.prod + (size_t)q0 * 32 + lane) : make_int2(0, 0);
+        for (int q = q0; q < q1; ++q) {
+            const unsigned it = (unsigned)(q - q0);
+            const int st = it & 1;
+            const int2 cur = pd;
+            if (q + 1 < q1) pd = __ldg(a.prod + (size_t)(q + 1) * 32 + lane);  // the next stage's descriptors, a stage early
+            if (it >= 2) mbar_wait(&bar_empty[st], ((it >> 1) - 1) & 1);
+            sweep_issue<PARTS>(sw_smem + (size_t)st * a.stage_smem, &bar_full[st], cur, a, B, bp, lane);
         }
         return;
     }
-    // ---- consumers ----------------------------------------------------------------------------------------------------
+    // ---- consumers ------------------------------------------------------------------------------------------------------
     const int g = lane >> 3, l = lane & 7, strip = warp * 4 + g;
     double2 acc[3][3][4];
 #pragma unroll
@@ -139,66 +190,19 @@ __global__ void __launch_bounds__((SW_WARPS + 1) * 32, 1)
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[f][r][i] = make_double2(0.0, 0.0);
-    unsigned it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const int q0 = __ldg(a.tile_ptr + tile), q1 = __ldg(a.tile_ptr + tile + 1);
-        for (int q = q0; q < q1; ++q, ++it) {
-            const int st = it & 1;
-            const unsigned char *sb = sw_smem + (size_t)st * a.stage_smem;
-            mbar_wait(&bar_full[st], (it >> 1) & 1);
-            const int *hdr = reinterpret_cast<const int *>(sb);
-            const int S = hdr[1], rotate = hdr[2], b_off = hdr[3];
-            const int Spad = (S + 3) & ~3;
-            const int *ul = reinterpret_cast<const int *>(sb + SW_HDR_INTS * 4) + strip * Spad;
-            const double *rec = reinterpret_cast<const double *>(sb + SW_HDR_INTS * 4 + SW_STRIPS * 4 * Spad) +
-                                (size_t)strip * S * SW_REC;
-            const double *bb = reinterpret_cast<const double *>(sb + b_off) + 2 * l;
-            int u = S > 0 ? ul[0] : 0;
-            for (int t = 0; t < S; ++t) {
-                const double *br = bb + u * SW_NODE;
-                if (t + 1 < S) u = ul[t + 1];
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    double av[10];
-#pragma unroll
-                    for (int h = 0; h < 5; ++h) {
-                        const double2 v = *reinterpret_cast<const double2 *>(rec + s * 10 + 2 * h);
-                        av[2 * h] = v.x;
-                        av[2 * h + 1] = v.y;
-                    }
-                    double2 bv[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) bv[i] = *reinterpret_cast<const double2 *>(br + s * 64 + 16 * i);
-#pragma unroll
-                    for (int f = 0; f < 3; ++f)
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                acc[f][r][i].x = fma(av[f * 3 + r], bv[i].x, acc[f][r][i].x);
-                                acc[f][r][i].y = fma(av[f * 3 + r], bv[i].y, acc[f][r][i].y);
-                            }
-                }
-                rec += SW_REC;
-            }
-            if (rotate) {
-                // end of a phase: the oldest row of the window (slot 0) is complete — store it and slide the window.
-                // The slots are RELATIVE (slot f = row q-1+f of the strip at phase q), so the slide is a register
-                // rotation (48 moves per 1944 FMAs); choosing the slot to store by a run-time index instead makes ptxas
-                // spill 40 accumulators around every stage.
-                sweep_flush(acc[0], hdr[SW_HDR_ROWS + strip], C, l);
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc[0][r][i] = acc[1][r][i];
-                        acc[1][r][i] = acc[2][r][i];
-                        acc[2][r][i] = make_double2(0.0, 0.0);
-                    }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[st]);
-        }
+    int rot = 0;
+    for (int q = q0; q < q1; ++q) {
+        const unsigned it = (unsigned)(q - q0);
+        const int st = it & 1;
+        const unsigned char *sb = sw_smem + (size_t)st * a.stage_smem;
+        mbar_wait(&bar_full[st], (it >> 1) & 1);
+        const int rotate = reinterpret_cast<const int *>(sb)[2];
+        if (rot == 0) sweep_stage<0>(acc, sb, strip, l, C);
+        else if (rot == 1) sweep_stage<1>(acc, sb, strip, l, C);
+        else sweep_stage<2>(acc, sb, strip, l, C);
+        if (rotate) rot = rot == 2 ? 0 : rot + 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
     }
 }
 
@@ -235,10 +239,10 @@ struct g4s_bsr_plan {
     std::vector<int> cuts;
     unsigned char *stream = nullptr;
     size_t stream_bytes = 0;
-    SweepStage *stages = nullptr;
+    int2 *prod = nullptr;    // copy descriptors, 32 per stage
     int nstages = 0;
-    int *tile_ptr = nullptr;
-    int ntiles = 0;
+    int *cta_ptr = nullptr;  // [grid + 1]
+    int grid = 0, ntiles = 0;
     long long *base = nullptr;
     int stage_smem = 0;
     long long total_steps = 0;  // strip-steps including padding (each moves 3 block slots)
@@ -365,8 +369,10 @@ void plan_tile(const int *browptr, const int *bcolids, const int *strip_ptr, con
 }
 
 struct HostPlan {
-    std::vector<SweepStage> stages;
-    std::vector<int> tile_ptr;
+    std::vector<SweepStage> stages;   // in execution order: CTA by CTA
+    std::vector<int> cta_ptr;         // [grid + 1]
+    std::vector<int> prod;            // 64 ints (32 x int2) per stage: what warp 0 needs to start the stage's copies
+    int ntiles = 0;
     std::vector<int> meta;            // per stage: header (64 ints) followed by the u lists
     std::vector<long long> meta_off;  // [nstages + 1]
     std::vector<long long> base;      // per block: index (in doubles) of its slot in the plan stream
@@ -375,7 +381,8 @@ struct HostPlan {
 };
 
 int build_host_plan(int mb, int kb, const int *rp, const int *ci, int nstrips, const int *strip_ptr, const int *strip_rows,
-                    int world, const int *cuts, HostPlan &hp) {
+                    int world, const int *cuts, int grid, int ctas_per_sm, HostPlan &hp) {
+    if (grid < 1 || ctas_per_sm < 1 || ctas_per_sm > 2) return fail(G4S_ERR_INVALID, "g4s_bsr3_plan: bad grid");
     if (mb < 0 || kb < 0 || !rp || world < 1 || world > 8 || (world > 1 && !cuts) || (nstrips > 0 && (!strip_ptr || !strip_rows)))
         return fail(G4S_ERR_INVALID, "g4s_bsr3_plan: bad arguments");
     const long long nb = mb ? rp[mb] : 0;
@@ -410,50 +417,69 @@ int build_host_plan(int mb, int kb, const int *rp, const int *ci, int nstrips, c
     }
     for (long long p = 0; p < nb; ++p)
         if (ci[p] < 0 || ci[p] >= kb) return fail(G4S_ERR_INVALID, "g4s_bsr3_plan: block column out of range");
-    const int smem_budget = ((227 * 1024 - 1024) / 2) & ~127;
-    static const int max_steps = [] {
+    // two stage buffers per CTA; with two CTAs per SM a stage holds a third of a phase of a mesh operator (3 of the 9
+    // columns of each strip: one line of the halo patch per strip row), with one CTA a whole phase
+    const int smem_budget = ((227 * 1024 / ctas_per_sm - 1024) / 2) & ~127;
+    static const int steps_env = [] {
         const char *e = getenv("G4S_BSR_SWEEP_STEPS");
-        return e ? std::max(1, atoi(e)) : 9;
+        return e && atoi(e) > 0 ? atoi(e) : 0;
     }();
+    const int max_steps = steps_env ? steps_env : (ctas_per_sm == 2 ? 3 : 9);
     const int ntiles = (nstrips + SW_STRIPS - 1) / SW_STRIPS;
     std::vector<std::vector<StageOut>> per_tile((size_t)ntiles);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int t = 0; t < ntiles; ++t)
         plan_tile(rp, ci, strip_ptr, strip_rows, t * SW_STRIPS, std::min(nstrips, (t + 1) * SW_STRIPS), world, cuts, smem_budget,
                   max_steps, per_tile[t]);
-    hp.tile_ptr.assign((size_t)ntiles + 1, 0);
-    for (int t = 0; t < ntiles; ++t) hp.tile_ptr[t + 1] = hp.tile_ptr[t] + (int)per_tile[t].size();
-    const int nstages = hp.tile_ptr[ntiles];
+    // execution order: CTA b sweeps tiles b, b + grid, ... (neighbouring tiles run at the same time on other SMs)
+    hp.ntiles = ntiles;
+    std::vector<const StageOut *> order;
+    hp.cta_ptr.assign((size_t)grid + 1, 0);
+    for (int b = 0; b < grid; ++b) {
+        for (int t = b; t < ntiles; t += grid)
+            for (const StageOut &so : per_tile[t]) order.push_back(&so);
+        hp.cta_ptr[b + 1] = (int)order.size();
+    }
+    const int nstages = (int)order.size();
     hp.stages.resize((size_t)nstages);
     hp.meta_off.assign((size_t)nstages + 1, 0);
+    hp.prod.assign((size_t)nstages * 64, 0);
     long long off = 0;
-    for (int t = 0, q = 0; t < ntiles; ++t)
-        for (const StageOut &so : per_tile[t]) {
-            const int cb = stage_chunk_bytes(so.S);
-            hp.stages[q].off = off;
-            hp.stages[q].chunk_bytes = cb;
-            hp.stages[q].tx_bytes = cb + so.U * SW_NODE * 8;
-            hp.meta_off[q + 1] = hp.meta_off[q] + SW_HDR_INTS + (long long)so.ulist.size();
-            hp.stage_smem = std::max(hp.stage_smem, round128(cb) + so.U * SW_NODE * 8);
-            off += cb;
-            hp.total_steps += (long long)SW_STRIPS * so.S;
-            ++q;
+    for (int q = 0; q < nstages; ++q) {
+        const StageOut &so = *order[q];
+        const int cb = stage_chunk_bytes(so.S);
+        hp.stages[q].off = off;
+        hp.stages[q].chunk_bytes = cb;
+        hp.stages[q].tx_bytes = cb + so.U * SW_NODE * 8;
+        hp.meta_off[q + 1] = hp.meta_off[q] + SW_HDR_INTS + (long long)so.ulist.size();
+        hp.stage_smem = std::max(hp.stage_smem, round128(cb) + so.U * SW_NODE * 8);
+        int *pd = hp.prod.data() + (size_t)q * 64;
+        int pre = 0;
+        for (int k = 0; k < so.hdr[0]; ++k) {
+            const int len = so.hdr[SW_HDR_RUNS + 2 * k + 1];
+            pd[2 * k] = so.hdr[SW_HDR_RUNS + 2 * k];
+            pd[2 * k + 1] = len | (pre << 8);
+            pre += len;
         }
+        pd[60] = (int)(unsigned)(off & 0xffffffffLL);
+        pd[61] = (int)(off >> 32);
+        pd[62] = cb;
+        pd[63] = hp.stages[q].tx_bytes;
+        off += cb;
+        hp.total_steps += (long long)SW_STRIPS * so.S;
+    }
     hp.stream_bytes = off;
     if (hp.stage_smem > smem_budget) return fail(G4S_ERR_INVALID, "g4s_bsr3_plan: a stage does not fit shared memory");
     hp.meta.resize((size_t)hp.meta_off[nstages]);
     hp.base.assign((size_t)nb, -1);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int t = 0; t < ntiles; ++t) {
-        int q = hp.tile_ptr[t];
-        for (const StageOut &so : per_tile[t]) {
-            int *m = hp.meta.data() + hp.meta_off[q];
-            std::memcpy(m, so.hdr, sizeof(int) * SW_HDR_INTS);
-            if (!so.ulist.empty()) std::memcpy(m + SW_HDR_INTS, so.ulist.data(), sizeof(int) * so.ulist.size());
-            const long long rec0 = (hp.stages[q].off + SW_HDR_INTS * 4 + (long long)so.ulist.size() * 4) / 8;
-            for (const auto &b : so.blocks) hp.base[b.first] = rec0 + b.second;
-            ++q;
-        }
+#pragma omp parallel for schedule(static)
+    for (int q = 0; q < nstages; ++q) {
+        const StageOut &so = *order[q];
+        int *m = hp.meta.data() + hp.meta_off[q];
+        std::memcpy(m, so.hdr, sizeof(int) * SW_HDR_INTS);
+        if (!so.ulist.empty()) std::memcpy(m + SW_HDR_INTS, so.ulist.data(), sizeof(int) * so.ulist.size());
+        const long long rec0 = (hp.stages[q].off + SW_HDR_INTS * 4 + (long long)so.ulist.size() * 4) / 8;
+        for (const auto &b : so.blocks) hp.base[b.first] = rec0 + b.second;
     }
     for (long long p = 0; p < nb; ++p)
         if (hp.base[p] < 0) return fail(G4S_ERR_INVALID, "g4s_bsr3_plan: internal error (unplaced block)");
@@ -467,8 +493,8 @@ extern "C" {
 int g4s_bsr3_plan_destroy(g4s_bsr_plan_t plan) {
     if (!plan) return G4S_OK;
     if (plan->stream) cudaFree(plan->stream);
-    if (plan->stages) cudaFree(plan->stages);
-    if (plan->tile_ptr) cudaFree(plan->tile_ptr);
+    if (plan->prod) cudaFree(plan->prod);
+    if (plan->cta_ptr) cudaFree(plan->cta_ptr);
     if (plan->base) cudaFree(plan->base);
     delete plan;
     return G4S_OK;
@@ -487,8 +513,14 @@ int g4s_bsr3_plan_create(g4s_bsr_plan_t *out, int mb, int kb, const int *browptr
     std::vector<int> ci((size_t)nb);
     if (nb) G4S_CUDA(cudaMemcpy(ci.data(), bcolids_dev, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost));
     HostPlan hp;
-    if ((rc = build_host_plan(mb, kb, rp.data(), ci.data(), nstrips, strip_ptr, strip_rows, world, cuts, hp))) return rc;
-    const int nstages = (int)hp.stages.size(), ntiles = (int)hp.tile_ptr.size() - 1;
+    static const int ctas_env = [] {
+        const char *e = getenv("G4S_BSR_SWEEP_CTAS");
+        return e ? atoi(e) : 1;
+    }();
+    const int ctas_per_sm = ctas_env == 2 ? 2 : 1, grid = ctas_per_sm * sm_count();
+    if ((rc = build_host_plan(mb, kb, rp.data(), ci.data(), nstrips, strip_ptr, strip_rows, world, cuts, grid, ctas_per_sm, hp)))
+        return rc;
+    const int nstages = (int)hp.stages.size(), ntiles = hp.ntiles;
     g4s_bsr_plan *pl = new g4s_bsr_plan();
     pl->mb = mb;
     pl->kb = kb;
@@ -498,6 +530,7 @@ int g4s_bsr3_plan_create(g4s_bsr_plan_t *out, int mb, int kb, const int *browptr
     pl->stream_bytes = (size_t)hp.stream_bytes;
     pl->nstages = nstages;
     pl->ntiles = ntiles;
+    pl->grid = grid;
     pl->stage_smem = hp.stage_smem;
     pl->total_steps = hp.total_steps;
     auto bail = [&](const char *what) {
@@ -506,28 +539,33 @@ int g4s_bsr3_plan_create(g4s_bsr_plan_t *out, int mb, int kb, const int *browptr
     };
     int *meta_dev = nullptr;
     long long *meta_off_dev = nullptr;
+    SweepStage *stages_dev = nullptr;
     if (cudaMalloc(&pl->stream, std::max<size_t>(pl->stream_bytes, 16)) != cudaSuccess) return bail("stream allocation");
-    if (cudaMalloc(&pl->stages, sizeof(SweepStage) * std::max(nstages, 1)) != cudaSuccess) return bail("stage table");
-    if (cudaMalloc(&pl->tile_ptr, sizeof(int) * ((size_t)ntiles + 1)) != cudaSuccess) return bail("tile table");
+    if (cudaMalloc(&pl->prod, sizeof(int2) * 32 * (size_t)std::max(nstages, 1)) != cudaSuccess) return bail("descriptor table");
+    if (cudaMalloc(&pl->cta_ptr, sizeof(int) * ((size_t)grid + 1)) != cudaSuccess) return bail("CTA table");
+    if (cudaMalloc(&stages_dev, sizeof(SweepStage) * std::max(nstages, 1)) != cudaSuccess) return bail("stage table");
     if (cudaMalloc(&pl->base, sizeof(long long) * std::max<long long>(nb, 1)) != cudaSuccess) return bail("block map");
     if (cudaMalloc(&meta_dev, sizeof(int) * std::max<size_t>(hp.meta.size(), 1)) != cudaSuccess) return bail("meta");
     if (cudaMalloc(&meta_off_dev, sizeof(long long) * ((size_t)nstages + 1)) != cudaSuccess) {
         cudaFree(meta_dev);
+        cudaFree(stages_dev);
         return bail("meta offsets");
     }
     cudaMemset(pl->stream, 0, std::max<size_t>(pl->stream_bytes, 16));
-    if (nstages) cudaMemcpy(pl->stages, hp.stages.data(), sizeof(SweepStage) * nstages, cudaMemcpyHostToDevice);
-    cudaMemcpy(pl->tile_ptr, hp.tile_ptr.data(), sizeof(int) * ((size_t)ntiles + 1), cudaMemcpyHostToDevice);
+    if (nstages) cudaMemcpy(stages_dev, hp.stages.data(), sizeof(SweepStage) * nstages, cudaMemcpyHostToDevice);
+    if (nstages) cudaMemcpy(pl->prod, hp.prod.data(), sizeof(int) * hp.prod.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->cta_ptr, hp.cta_ptr.data(), sizeof(int) * ((size_t)grid + 1), cudaMemcpyHostToDevice);
     if (nb) cudaMemcpy(pl->base, hp.base.data(), sizeof(long long) * (size_t)nb, cudaMemcpyHostToDevice);
     if (!hp.meta.empty()) cudaMemcpy(meta_dev, hp.meta.data(), sizeof(int) * hp.meta.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(meta_off_dev, hp.meta_off.data(), sizeof(long long) * ((size_t)nstages + 1), cudaMemcpyHostToDevice);
     if (nstages) {
-        sweep_scatter_meta_kernel<<<nstages, 128>>>(meta_dev, meta_off_dev, pl->stages, nstages, pl->stream);
+        sweep_scatter_meta_kernel<<<nstages, 128>>>(meta_dev, meta_off_dev, stages_dev, nstages, pl->stream);
         count_launch();
     }
     const cudaError_t e = cudaDeviceSynchronize();
     cudaFree(meta_dev);
     cudaFree(meta_off_dev);
+    cudaFree(stages_dev);
     if (e != cudaSuccess) return bail(cudaGetErrorString(e));
     *out = pl;
     return G4S_OK;
@@ -536,16 +574,17 @@ int g4s_bsr3_plan_create(g4s_bsr_plan_t *out, int mb, int kb, const int *browptr
 // The schedule alone, from HOST arrays, without touching a device: what the CPU tests replay step by step
 // (tests/test_bsr_plan_cpu.py).  Arrays are malloc'd (g4s_free).
 int g4s_bsr3_plan_inspect_host(int mb, int kb, const int *browptr, const int *bcolids, int nstrips, const int *strip_ptr,
-                               const int *strip_rows, int world, const int *cuts, int *nstages, int *ntiles,
-                               long long *stream_bytes, int *stage_smem_bytes, double *slot_fill, long long **stage_table,
-                               int **tile_ptr, int **meta, long long **meta_off, long long **base) {
+                               const int *strip_rows, int world, const int *cuts, int grid, int ctas_per_sm, int *nstages,
+                               int *ntiles, long long *stream_bytes, int *stage_smem_bytes, double *slot_fill,
+                               long long **stage_table, int **cta_ptr, int **prod, int **meta, long long **meta_off,
+                               long long **base) {
     if (!browptr || mb < 0) return fail(G4S_ERR_INVALID, "g4s_bsr3_plan_inspect_host: bad arguments");
     HostPlan hp;
-    int rc = build_host_plan(mb, kb, browptr, bcolids, nstrips, strip_ptr, strip_rows, world, cuts, hp);
+    int rc = build_host_plan(mb, kb, browptr, bcolids, nstrips, strip_ptr, strip_rows, world, cuts, grid, ctas_per_sm, hp);
     if (rc) return rc;
     const long long nb = mb ? browptr[mb] : 0;
     if (nstages) *nstages = (int)hp.stages.size();
-    if (ntiles) *ntiles = (int)hp.tile_ptr.size() - 1;
+    if (ntiles) *ntiles = hp.ntiles;
     if (stream_bytes) *stream_bytes = hp.stream_bytes;
     if (stage_smem_bytes) *stage_smem_bytes = hp.stage_smem;
     if (slot_fill) *slot_fill = hp.total_steps ? (double)nb / (3.0 * (double)hp.total_steps) : 1.0;
@@ -558,7 +597,8 @@ int g4s_bsr3_plan_inspect_host(int mb, int kb, const int *browptr, const int *bc
         static_assert(sizeof(SweepStage) == 16, "stage table entries are two 64-bit words");
         *stage_table = (long long *)dup(hp.stages.data(), sizeof(SweepStage) * hp.stages.size());
     }
-    if (tile_ptr) *tile_ptr = (int *)dup(hp.tile_ptr.data(), sizeof(int) * hp.tile_ptr.size());
+    if (cta_ptr) *cta_ptr = (int *)dup(hp.cta_ptr.data(), sizeof(int) * hp.cta_ptr.size());
+    if (prod) *prod = (int *)dup(hp.prod.data(), sizeof(int) * hp.prod.size());
     if (meta) *meta = (int *)dup(hp.meta.data(), sizeof(int) * hp.meta.size());
     if (meta_off) *meta_off = (long long *)dup(hp.meta_off.data(), sizeof(long long) * hp.meta_off.size());
     if (base) *base = (long long *)dup(hp.base.data(), sizeof(long long) * hp.base.size());
@@ -597,9 +637,8 @@ static int sweep_launch(g4s_bsr_plan_t plan, const double *B_dev, const BParts &
     if (rc) return rc;
     SweepArgs a;
     a.stream = plan->stream;
-    a.stages = plan->stages;
-    a.tile_ptr = plan->tile_ptr;
-    a.ntiles = plan->ntiles;
+    a.prod = plan->prod;
+    a.cta_ptr = plan->cta_ptr;
     a.stage_smem = plan->stage_smem;
     const int smem = 2 * plan->stage_smem;
     auto k0 = bsr3_sweep_kernel<false>;
@@ -610,7 +649,7 @@ static int sweep_launch(g4s_bsr_plan_t plan, const double *B_dev, const BParts &
         G4S_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured.done(smem);
     }
-    const int grid = std::min(plan->ntiles, sm_count());
+    const int grid = plan->grid;  // fixed by the plan: every CTA's stages are stored consecutively
     if (parts) k1<<<grid, (SW_WARPS + 1) * 32, smem, st>>>(a, nullptr, bp, C_dev);
     else k0<<<grid, (SW_WARPS + 1) * 32, smem, st>>>(a, B_dev, bp, C_dev);
     G4S_CHECK_LAUNCH("bsr3_sweep_kernel");

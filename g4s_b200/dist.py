@@ -393,7 +393,10 @@ class DistBsrSpMM:
     straight over NVLink (g4s_bsr3_spmm64_partitioned_device).  No halo exchange and no replicated B: at the
     256^3-node size of BASELINE config 5, B is 25.8 GB and a replica per GPU would cost more than the matrix."""
 
-    def __init__(self, browptr, bcolids, bvalues, cuts, group=None, row_order=None):
+    def __init__(self, browptr, bcolids, bvalues, cuts, group=None, row_order=None, strips=None, kb=None):
+        """strips = (strip_ptr, strip_rows) of the LOCAL block rows (g4s_b200.bsr.grid_pencil_strips) switches the product
+        to the sliding-window sweep (g4s_bsr3_plan_*): the plan is built here, once, and packs the block values; call
+        repack() after changing bvalues."""
         self.row_order = row_order  # optional device int32 permutation of the local block rows (tile-major schedule)
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
@@ -424,13 +427,39 @@ class DistBsrSpMM:
             .view(self.mb * 3, 64)
         self._cuts_c = (C.c_int * (self.world + 1))(*self.cuts)
         self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.plan = None
+        if strips is not None:
+            from .bsr import BsrPlan
+
+            self.plan = BsrPlan(self.mb, self.cuts[-1] if kb is None else kb, browptr.data_ptr(), bcolids.data_ptr(), strips,
+                                self.world, self.cuts)
+            self.plan.set_values(bvalues.data_ptr())
+            torch.cuda.synchronize()
         dist.barrier(group=self.group)
+
+    def repack(self):
+        """New block values (same pattern): pack them into the sweep plan again."""
+        if self.plan is not None:
+            self.plan.set_values(self.bvalues.data_ptr(), torch.cuda.current_stream())
+
+    def begin_update(self):
+        """Call BEFORE writing new contents into B_local: a 4-byte all-reduce on the current stream orders the write after
+        every peer's previous product, which reads this rank's slice over NVLink.  (apply(sync=True) only orders a product
+        after the peers' WRITES; without this second point a fast rank would overwrite its slice while a slower peer's
+        kernel is still reading it.)  Returns B_local."""
+        dist.all_reduce(self._flag, group=self.group)
+        return self.B_local
 
     def apply(self, C_local, sync=True):
         """C_local[local_block_rows * 3, 64] = (A B)[owned rows].  sync=True orders the product after every rank's
-        writes to its slice of B with a 4-byte all-reduce on the current stream."""
+        writes to its slice of B with a 4-byte all-reduce on the current stream.  That is ONE of the two ordering points
+        an iteration needs: before B_local is modified again call begin_update() (or order the write after all ranks'
+        products by other means)."""
         if sync:
             dist.all_reduce(self._flag, group=self.group)
+        if self.plan is not None:
+            self.plan.spmm_partitioned(self._parts, C_local.data_ptr(), torch.cuda.current_stream())
+            return C_local
         if self.row_order is not None:
             check(lib().g4s_bsr3_spmm64_partitioned_ordered_device(
                 C.c_int(self.mb), C.c_void_p(self.browptr.data_ptr()), C.c_void_p(self.bcolids.data_ptr()),
@@ -445,6 +474,9 @@ class DistBsrSpMM:
         return C_local
 
     def close(self):
+        if self.plan is not None:
+            self.plan.destroy()
+            self.plan = None
         if self._own:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)

@@ -316,14 +316,16 @@ int g4s_bsr3_plan_spmm64_partitioned_device(g4s_bsr_plan_t plan, int world, cons
 int g4s_bsr3_plan_info(g4s_bsr_plan_t plan, double *slot_fill, long long *stream_bytes, int *nstages, int *ntiles,
                        int *stage_smem_bytes);
 int g4s_bsr3_plan_destroy(g4s_bsr_plan_t plan);
-/* The schedule alone, built from HOST arrays without touching a device (what the CPU tests replay): per stage the
- * table entry (byte offset in the plan stream, chunk bytes | expected bytes << 32), per tile its first stage, the
+/* The schedule alone, built from HOST arrays without touching a device (what the CPU tests replay), for a launch of
+ * `grid` CTAs at ctas_per_sm (1 or 2) per SM: per stage, in execution order, the table entry (byte offset in the plan
+ * stream, chunk bytes | expected bytes << 32) and the 64-int row of copy descriptors, per CTA its first stage, the
  * concatenated stage headers + position lists (`meta`, stage q at meta_off[q]), and per block the index (in doubles) of its
  * slot in the plan stream.  Output arrays are malloc'd (g4s_free); any of the pointers may be null. */
 int g4s_bsr3_plan_inspect_host(int mb, int kb, const int *browptr, const int *bcolids, int nstrips, const int *strip_ptr,
-                               const int *strip_rows, int world, const int *cuts, int *nstages, int *ntiles,
-                               long long *stream_bytes, int *stage_smem_bytes, double *slot_fill, long long **stage_table,
-                               int **tile_ptr, int **meta, long long **meta_off, long long **base);
+                               const int *strip_rows, int world, const int *cuts, int grid, int ctas_per_sm, int *nstages,
+                               int *ntiles, long long *stream_bytes, int *stage_smem_bytes, double *slot_fill,
+                               long long **stage_table, int **cta_ptr, int **prod, int **meta, long long **meta_off,
+                               long long **base);
 /* Strips for the nodes k_begin <= k < k_end of an n0 x n1 x n2 grid numbered n0 fastest, as LOCAL row numbers
  * ((k - k_begin)*n1 + j)*n0 + i: one strip per grid line along the third axis, the lines of a p0 x p1 patch consecutive
  * (p0 = p1 = 4: one patch per tile).  strip_ptr (host) receives n0*n1 + 1 offsets, strip_rows n0*n1*(k_end-k_begin) rows. */

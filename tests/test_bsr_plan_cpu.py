@@ -25,9 +25,10 @@ def replay(mb, rp, ci, blocks, Bd, plan, world=1, cuts=None):
             for s in range(3):
                 stream[base[p] + 10 * s + r] = blocks[p, r, s]
     C = np.full((mb * 3, 64), np.nan)
-    for t in range(plan["ntiles"]):
+    assert plan["cta_ptr"][0] == 0 and plan["cta_ptr"][-1] == plan["nstages"]
+    for t in range(plan["grid"]):
         acc = np.zeros((STRIPS, 3, 3, 64))
-        for q in range(plan["tile_ptr"][t], plan["tile_ptr"][t + 1]):
+        for q in range(plan["cta_ptr"][t], plan["cta_ptr"][t + 1]):
             off, packed = plan["stage_table"][q]
             chunk, tx = int(packed & 0xffffffff), int(packed >> 32)
             h = ints[off // 4: off // 4 + HDR]
@@ -35,8 +36,12 @@ def replay(mb, rp, ci, blocks, Bd, plan, world=1, cuts=None):
             spad = (S + 3) & ~3
             assert chunk == HDR * 4 + STRIPS * 4 * spad + STRIPS * S * REC * 8 and b_off == (chunk + 127) & ~127
             staged = []
+            pd = plan["prod"][q]                   # what warp 0 reads to start the stage's copies
+            assert (int(pd[60]) & 0xffffffff) | (int(pd[61]) << 32) == off and pd[62] == chunk and pd[63] == tx
+            assert not pd[2 * nruns:60].any() and nruns <= 30
             for k in range(nruns):
                 j0, ln = int(h[RUNS + 2 * k]), int(h[RUNS + 2 * k + 1])
+                assert pd[2 * k] == j0 and pd[2 * k + 1] == ln | (len(staged) << 8) and 0 < ln < 256
                 if world > 1:  # a run never straddles two owners of B
                     assert np.searchsorted(cuts, j0, side="right") == np.searchsorted(cuts, j0 + ln - 1, side="right")
                 staged += list(range(j0, j0 + ln))
@@ -79,9 +84,9 @@ def stencil_bsr(n0, n1, n2, rng):
     return pat.indptr.astype(np.int32), pat.indices.astype(np.int32), rng.uniform(-1, 1, (pat.nnz, 3, 3))
 
 
-def check(oracle, mb, rp, ci, blocks, strips, world=1, cuts=None, min_fill=0.0):
+def check(oracle, mb, rp, ci, blocks, strips, world=1, cuts=None, min_fill=0.0, grid=5, ctas=2):
     Bd = np.random.default_rng(3).uniform(-1, 1, (mb * 3, 64))
-    plan = bsr.inspect_host(mb, mb, rp, ci, strips, world, cuts)
+    plan = bsr.inspect_host(mb, mb, rp, ci, strips, world, cuts, grid, ctas)
     got = replay(mb, rp, ci, blocks, Bd, plan, world, cuts)
     want = oracle.bsr_spmm(rp, ci, blocks.reshape(-1), 3, Bd)
     absw = oracle.bsr_spmm(rp, ci, np.abs(blocks).reshape(-1), 3, np.abs(Bd))
@@ -97,8 +102,10 @@ def test_mesh_operator_swept_along_grid_lines(oracle):
     rp, ci, blocks = stencil_bsr(n0, n1, n2, rng)
     strips = bsr.grid_pencil_strips(n0, n1, 0, n2)
     assert np.array_equal(np.sort(strips[1]), np.arange(n0 * n1 * n2)) and len(strips[0]) == n0 * n1 + 1
-    plan = check(oracle, n0 * n1 * n2, rp, ci, blocks, strips, min_fill=0.6)
     # interior lines load every row of B once for three blocks; the mesh boundary and the partly filled last tile cost the rest
+    plan = check(oracle, n0 * n1 * n2, rp, ci, blocks, strips, min_fill=0.6, grid=3, ctas=2)
+    assert plan["stage_smem_bytes"] <= (227 * 1024 // 2 - 1024) // 2
+    plan = check(oracle, n0 * n1 * n2, rp, ci, blocks, strips, min_fill=0.6, grid=2, ctas=1)  # whole phases per stage
     assert plan["stage_smem_bytes"] <= (227 * 1024 - 1024) // 2
 
 
@@ -139,7 +146,7 @@ def test_partitioned_plan_cuts_runs_at_owner_boundaries(oracle):
     lci, lbl = ci[rp[r0]:rp[r1]], blocks[rp[r0]:rp[r1]]
     strips = bsr.grid_pencil_strips(n0, n1, 3, 6)
     Bd = rng.uniform(-1, 1, (mb * 3, 64))
-    plan = bsr.inspect_host(r1 - r0, mb, lrp, lci, strips, 3, cuts)
+    plan = bsr.inspect_host(r1 - r0, mb, lrp, lci, strips, 3, cuts, grid=4)
     got = replay(r1 - r0, lrp, lci, lbl, Bd, plan, 3, np.array(cuts))
     want = oracle.bsr_spmm(rp, ci, blocks.reshape(-1), 3, Bd)[r0 * 3:r1 * 3]
     assert np.allclose(got, want, rtol=0, atol=1e-12 * 27 * 3)
