@@ -7,7 +7,9 @@
  * zero here, the reference leaves it uninitialised), sets B = 1.0 (mv/mv.c:65-67) and times the four entry points
  * in the reference's order (dsymv, dtrmv, sspmv, dgemv; dtrmv overwrites B for the two calls after it).  Differences,
  * on purpose: the size line is parsed from the first non-comment line (the reference discards that line and reads the
- * next one), and times are wall-clock milliseconds (the reference uses clock(), i.e. CPU time). */
+ * next one), and times are wall-clock milliseconds (the reference uses clock(), i.e. CPU time).
+ * With G4S_MV_DUMP=<path> the four results (C after dsymv, B after dtrmv, C after sspmv, C after dgemv; dim doubles
+ * each) are written to <path>: tests/test_drivers.py compares them with the reference's own mv.c functions. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,18 +62,27 @@ int main(int argc, char *argv[]) {
 
     matrix_multiply_dgemv(A, B, C, 1);  /* warm-up: CUDA context creation is not part of any timing */
     for (int i = 0; i < dim; i++) B[i] = 1.0;
+    const char *dump_path = getenv("G4S_MV_DUMP");
+    FILE *dump = dump_path ? fopen(dump_path, "wb") : NULL;
     double t0 = now_ms();
     matrix_multiply_dsymv(A, B, C, dim);
     printf("matrix_multiply_dsymv time: %f ms\n", now_ms() - t0);
+    if (dump) fwrite(C, sizeof(double), dim, dump);
     t0 = now_ms();
     matrix_multiply_dtrmv(A, B, C, dim);
     printf("matrix_multiply_dtrmv time: %f ms\n", now_ms() - t0);
+    if (dump) fwrite(B, sizeof(double), dim, dump);
     t0 = now_ms();
     matrix_multiply_sspmv(A, B, C, dim);
     printf("matrix_multiply_sspmv time: %f ms\n", now_ms() - t0);
+    if (dump) fwrite(C, sizeof(double), dim, dump);
     t0 = now_ms();
     matrix_multiply_dgemv(A, B, C, dim);
     printf("matrix_multiply_dgemv time: %f ms\n", now_ms() - t0);
+    if (dump) {
+        fwrite(C, sizeof(double), dim, dump);
+        fclose(dump);
+    }
     double sum = 0.0;
     for (int i = 0; i < dim; i++) sum += C[i];
     printf("checksum(C) %.17g\n", sum);

@@ -416,22 +416,27 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
         }
         return;
     }
-    if (PART) {
-        // A chunk that touches another GPU's slice: NVLink loads cost microseconds, so they are not chained into
-        // the row sums.  First every staged value is multiplied by its x entry, 32 consecutive nonzeros per step
-        // with all loads of a step batch independent (many in flight per lane); the row sums below then read
-        // finished products out of shared memory.
+    // FLAT: gather first, sum afterwards.  Every staged value is multiplied by its x entry in one flat sweep over the
+    // chunk — 32 consecutive nonzeros per step, 8 steps in flight per lane, all loads independent of the row structure —
+    // and the row sums below read finished products out of shared memory.  Used for chunks that touch another GPU's
+    // slice: NVLink loads cost microseconds and must not be chained into the row sums.  (Measured for the 256-nnz chunks of
+    // power-law graphs too, where a lane owns one or two nonzeros of a row: R-MAT 24 1.315 -> 1.385 ms.  That kernel does
+    // not wait for gathers in flight; it sits on the L2's request rate — 263 M distinct 32-byte sectors per product over
+    // ~96 slices at one request per clock is 1.39 ms — profiles/r02_rmat_summary.md.)
+    // The products are rounded before they are added (no FMA chain): within the parity bound 1e-12 sum|a||x|.
+    constexpr bool FLAT = PART;
+    if (FLAT) {
         double *pv = const_cast<double *>(buf.vals);
         const int kb = nnz0 - a0, kend = nnz1 - a0;
         int k = kb + lane;
         for (; k + 7 * 32 < kend; k += 8 * 32) {
             double xv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = *x_part_ptr(xp, buf.cols[k + u * 32]);
+            for (int u = 0; u < 8; ++u) xv[u] = PART ? *x_part_ptr(xp, buf.cols[k + u * 32]) : __ldg(x + buf.cols[k + u * 32]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) pv[k + u * 32] *= xv[u];
         }
-        for (; k < kend; k += 32) pv[k] *= *x_part_ptr(xp, buf.cols[k]);
+        for (; k < kend; k += 32) pv[k] *= PART ? *x_part_ptr(xp, buf.cols[k]) : __ldg(x + buf.cols[k]);
         __syncwarp();
     }
     for (int base = 0; base < nloc; base += PER_PASS) {
@@ -449,7 +454,7 @@ __device__ __forceinline__ void chunk_rows(const ChunkBuf<CAP> &buf, const SpmvA
         int k = s + sub - a0;
         const int ke = e - a0;
 #pragma unroll 4
-        for (; k < ke; k += L) acc = PART ? acc + buf.vals[k] : fma(buf.vals[k], __ldg(x + buf.cols[k]), acc);
+        for (; k < ke; k += L) acc = FLAT ? acc + buf.vals[k] : fma(buf.vals[k], __ldg(x + buf.cols[k]), acc);
 #pragma unroll
         for (int o = L >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (sub == 0 && r < nloc) {

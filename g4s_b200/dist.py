@@ -359,9 +359,13 @@ class DistSpGEMM:
                                               C.c_void_p(0)))
             self.B = CSR._from_handle(h)
 
-    def multiply(self):
-        """Returns (C_local, global_nnz_offset): this rank's rows of C and where they start in the global CSR."""
+    def multiply(self, offsets=True):
+        """Returns (C_local, global_nnz_offset): this rank's rows of C and where they start in the global CSR.
+        offsets=False skips the all-gather of the per-rank nnz (a collective plus a host read per product) and returns
+        (C_local, None): C stays distributed, and a loop that only needs the local rows never leaves the GPU."""
         C_local = HashSpGEMM(self.A_local, self.B)
+        if not offsets:
+            return C_local, None
         dev = torch.device("cuda", torch.cuda.current_device())
         mine = torch.full((1,), C_local.nnz, dtype=torch.int64, device=dev)  # a fill kernel: no pageable copy, no sync
         every = torch.empty(self.world, dtype=torch.int64, device=dev)

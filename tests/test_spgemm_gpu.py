@@ -195,3 +195,30 @@ def test_full_size_config4_properties(g4s):
     Eh = g4s.OuterSpGEMM(A, A).to_host()
     assert np.array_equal(Eh.rowptr, Ch.rowptr) and np.array_equal(Eh.colids, Ch.colids)
     assert np.array_equal(Eh.values, Ch.values)
+
+
+def test_repeated_product_reuses_host_decisions_and_survives_a_changed_pattern(g4s, oracle):
+    """The second product of the same handles launches with the first one's class counts / nnz(C) and has the device
+    confirm them (spgemm.cu: SpgemmGuess): same C.  When the operand's PATTERN is then changed in place under the same
+    handle and the same nnz, the confirmation fails on the device and the product must fall back and still be exact."""
+    import torch
+
+    from g4s_b200.dist import _DevArray
+
+    A = powerlaw_csr(3000, 4, max_deg=400)
+    Bt = random_csr(3000, 2500, 0.004, 5)
+    Ad, Bd = as_csr(g4s, A), as_csr(g4s, Bt)
+    rpt, col, val, scale = oracle_product(oracle, A, Bt)
+    for _ in range(3):
+        check_against(g4s.HashSpGEMM(Ad, Bd).to_host(), rpt, col, val, scale)
+    # rewrite A's column ids in place: reverse every row's columns end-for-end across the matrix width
+    _, ci, _ = Ad.device_arrays()
+    view = torch.as_tensor(_DevArray(ci, len(A[3]), "<i4"), device="cuda")
+    new_cols = (A[1] - 1 - A[3]).astype(np.int32)
+    A2 = (A[0], A[1], A[2], new_cols, A[4])           # rows now unsorted as well: a different class mix
+    view.copy_(torch.from_numpy(new_cols).cuda())
+    torch.cuda.synchronize()
+    rpt2, col2, val2, scale2 = oracle_product(oracle, A2, Bt)
+    assert not np.array_equal(rpt, rpt2)
+    for _ in range(2):
+        check_against(g4s.HashSpGEMM(Ad, Bd).to_host(), rpt2, col2, val2, scale2)
