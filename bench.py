@@ -107,13 +107,39 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs
-def cpu_spmv_sample(oracle, min_seconds, steps=None, warmup=1):
+def cpu_rows_for_this_box():
+    """The CPU arm runs the WHOLE configs[1] matrix (64 M rows: 20.6 GB of CSR + 1 GB of vectors on the host) when the box
+    has the memory for it, else the first CPU_SAMPLE_ROWS rows.  Both arms evaluate this the same way, so their `config`
+    blocks agree."""
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    return N_GRID ** 3 if avail >= 48e9 else CPU_SAMPLE_ROWS
+
+
+def workload_config(n=N_GRID):
+    """`config` of both arms: the workload, nothing about how an arm runs it."""
+    rows, nnz = n ** 3, (3 * n - 2) ** 3
+    cpu_rows = cpu_rows_for_this_box() if n == N_GRID else None
+    cfg = {"workload": "SpMV y=Ax, 3-D 27-point Laplacian n=%d (BASELINE configs[1])" % n, "rows": rows, "nnz": nnz,
+           "index_dtype": "int32", "bytes_per_step": spmv_bytes(rows, rows, nnz),
+           "l2": "inputs (21.9 GB over all GPUs) exceed the 126 MB L2; no flush"}
+    if cpu_rows is not None and cpu_rows != rows:
+        cfg["workload"] += "; the CPU arm runs a bounded sample per step (first %d rows: host memory)" % cpu_rows
+        cfg["cpu_arm_rows"] = cpu_rows
+    return cfg
+
+
+def cpu_spmv_sample(oracle, min_seconds, steps=None, warmup=1, rows=None):
     """The oracle's OpenMP CSR SpMV (port of "y = A x", mv/mv.c:23-27, on mm/inc/CSR.h's container — the
-    reference's own mv is dense MKL and cannot hold this matrix) on the first CPU_SAMPLE_ROWS rows of the
-    same 27-point matrix, all host threads.  Returns (GB/s, seconds per pass, description)."""
-    rows = CPU_SAMPLE_ROWS
+    reference's own mv is dense MKL and cannot hold this matrix) on the first `rows` rows of the same 27-point matrix
+    (all of them when the host has the memory), all host threads.  Returns (GB/s, seconds per pass, description)."""
+    rows = cpu_rows_for_this_box() if rows is None else rows
     A = oracle.gen_laplacian3d27(N_GRID, 0, rows)
-    ncols_touched = rows + N_GRID * N_GRID + N_GRID + 1  # x entries the sample reads
+    ncols_touched = min(N_GRID ** 3, rows + N_GRID * N_GRID + N_GRID + 1)  # x entries these rows read
     x = np.random.default_rng(12345).uniform(-1.0, 1.0, A[1])
     nnz = len(A[3])
     nbytes = 12.0 * nnz + 4.0 * (rows + 1) + 8.0 * ncols_touched + 8.0 * rows
@@ -126,8 +152,8 @@ def cpu_spmv_sample(oracle, min_seconds, steps=None, warmup=1):
         el = time.perf_counter() - t0
         if (steps is not None and n >= steps) or (steps is None and el >= min_seconds):
             break
-    desc = ("rows [0,%d) of the n=%d 27-point Laplacian (%d nnz, %.2f GB algorithmic), %d passes of the "
-            "OpenMP CSR row loop" % (rows, N_GRID, nnz, nbytes / 1e9, n))
+    desc = ("%s of the n=%d 27-point Laplacian (%d nnz, %.2f GB algorithmic), %d passes of the OpenMP CSR row loop"
+            % ("all %d rows" % rows if rows == N_GRID ** 3 else "rows [0,%d)" % rows, N_GRID, nnz, nbytes / 1e9, n))
     return nbytes * n / el / 1e9, el / n, desc
 
 
@@ -159,15 +185,12 @@ def run_reference(args, rank):
 
     oracle = Oracle()
     cores = oracle.omp_max_threads()
-    for _ in range(max(args.warmup - 1, 0)):
-        pass
     gbs, sec, desc = cpu_spmv_sample(oracle, 0.0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SpMV y=Ax, 3-D 27-point Laplacian n=%d (BASELINE configs[1]); CPU arm runs a "
-                               "bounded sample per step" % N_GRID, "rows": N_GRID ** 3, "sample_rows": CPU_SAMPLE_ROWS},
+        "config": workload_config(),
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -447,20 +470,28 @@ def run_ours(args, rank, world):
     # duration inside the timed region (the fix-up / halo kernels are inside that time, so this is conservative)
     per_gpu_bytes = total_bytes / world
     achieved = per_gpu_bytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of the kernel comes from an ncu capture (it cannot be measured live); the capture records the SHA-256 of
+    # the kernel's source file, and a capture of another build is not reported
+    traffic, traffic_src = None, None
     try:
+        import hashlib
+
         with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch") if world == 1 and n == N_GRID else None
+            tj = json.load(f)
+        with open(os.path.join(ROOT, "g4s_b200", "csrc", "spmv.cu"), "rb") as f:
+            same_build = hashlib.sha256(f.read()).hexdigest() == tj.get("spmv_cu_sha256")
+        if world == 1 and n == N_GRID and same_build:
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("kernel", "") + " — " + tj.get("capture", "")
+        elif world == 1 and n == N_GRID:
+            traffic_src = "stale: profiles/spmv_traffic.json was captured from another build of spmv.cu"
     except Exception:
         pass
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SpMV y=Ax, 3-D 27-point Laplacian n=%d (BASELINE configs[1])" % n,
-                   "rows": rows_total, "nnz": nnz_total, "index_dtype": "int32", "bytes_per_step": total_bytes,
-                   "parallelism": parallelism, "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush"
-                   % (per_gpu_bytes / 1e9)},
+        "config": workload_config(n),
+        "parallelism": parallelism,
         "gflops": 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9,
         "pct_of_8TBs": value / world / 8000.0 * 100.0,
         "clocks": clocks,
@@ -473,7 +504,8 @@ def run_ours(args, rank, world):
         "step_ms": step_ms,
         "parity_check": parity,
         "roofline": {"bound": "hbm", "kernel": "spmv_chunk_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic},
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                     "traffic_source": traffic_src},
     }
     if spgemm_multi is not None:
         line["spgemm"] = spgemm_multi
@@ -498,6 +530,14 @@ def run_ours(args, rank, world):
                 line["other_configs"] = bench_other_configs(g4s_b200, torch, peak)
             except Exception as e:  # the headline line must not depend on the riders
                 line["other_configs"] = {"error": str(e)[:200]}
+            try:
+                line["dense_mv"] = bench_dense_mv(g4s_b200, torch, peak)
+            except Exception as e:
+                line["dense_mv"] = {"error": str(e)[:200]}
+            try:
+                line["opt_matmul"] = bench_opt_matmul(g4s_b200, torch)
+            except Exception as e:
+                line["opt_matmul"] = {"error": str(e)[:200]}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -698,6 +738,100 @@ def bench_bsr(g4s_b200, torch, dist, rank, world, peak, steps=10):
     else:
         op.close()
     P.make_empty()
+    return out
+
+
+def bench_dense_mv(g4s_b200, torch, peak, dim=16384):
+    """the literal mv/mv.c entry points (mv/mv.c:6-27) at a dense-feasible size.  GPU: the four
+    operations on device-resident buffers (g4s_dense_mv_device; CUDA events, 3 warm-ups, 10 launches), bytes = the stored
+    elements each one must read (8 dim^2 for dgemv, 4 dim (dim+1) for the triangular / symmetric ones) + the vectors.
+    CPU: the reference's own matrix_multiply_* (oracle/_ref/libmv_ref.so = unmodified mv/mv.c on OpenBLAS, the MKL stand-in;
+    the oracle's restatement when that library is absent), one call after one warm-up, all host threads OpenBLAS uses."""
+    import ctypes as C
+
+    from g4s_b200._lib import check
+    from oracle.binding import Oracle, Ref
+
+    L = g4s_b200.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand(dim * dim, dtype=torch.float64, device="cuda", generator=g)
+    B = torch.ones(dim, dtype=torch.float64, device="cuda")
+    Cv = torch.empty(dim, dtype=torch.float64, device="cuda")
+    try:
+        ref = Ref()
+        impl, kind = (ref, "reference") if ref.mv_available else (Oracle(), "port")
+    except Exception:
+        impl, kind = Oracle(), "port"
+    Ah = A.cpu().numpy()
+    out = {"dim": dim, "cpu_kind": kind, "note": "dense dim x dim buffer as mv/mv.c builds it; dtrmv works in place on B"}
+    for op, name, cpu_name, nbytes in ((0, "dgemv", "dgemv", 8.0 * dim * dim + 16.0 * dim),
+                                       (1, "dsymv", "dsymv", 4.0 * dim * (dim + 1) + 16.0 * dim),
+                                       (2, "dtrmv", "dtrmv", 4.0 * dim * (dim + 1) + 16.0 * dim),
+                                       (3, "sspmv", "sspmv" if kind == "reference" else "dspmv", 4.0 * dim * (dim + 1) + 16.0 * dim)):
+        def run():
+            if op == 2:
+                B.fill_(1.0 / dim)
+            check(L.g4s_dense_mv_device(C.c_int(op), C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()),
+                                        C.c_void_p(Cv.data_ptr()), C.c_int(dim), C.c_void_p(0)))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        Bh = np.full(dim, 1.0 / dim)
+        impl.dense_mv(cpu_name, Ah, Bh)
+        t0 = time.perf_counter()
+        impl.dense_mv(cpu_name, Ah, Bh)
+        cpu_s = time.perf_counter() - t0
+        out["matrix_multiply_" + name] = {"gpu_ms": ms, "gpu_gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                                          "cpu_ms": cpu_s * 1e3, "cpu_gbs": nbytes / cpu_s / 1e9}
+    return out
+
+
+def bench_opt_matmul(g4s_b200, torch):
+    """OptMatmul res = xx w (deepmd/source/op/opt_matmul.cc:24-62) at the layer shapes of a DeePMD
+    model (fitting net 240 x 240, embedding net 25 -> 50 -> 100) for M = atoms x frames rows.  GPU: device-resident, CUDA
+    events, 3 warm-ups, 10 launches.  CPU: the reference's own engine loop (GraphProcess of deepmd/source/op/graph.h with the
+    op's gather; 8 OpenMP threads, as the reference pins them) on the first 8192 rows."""
+    from g4s_b200.opt_matmul import opt_matmul_device
+    from oracle.binding import Oracle, Ref
+
+    try:
+        ref = Ref()
+        impl, kind = (ref, "reference") if ref.available and hasattr(ref.lib, "ref_opt_matmul") else (Oracle(), "port")
+    except Exception:
+        impl, kind = Oracle(), "port"
+    out = {"cpu_kind": kind, "cpu_rows": 8192}
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for M, N, K in ((131072, 240, 240), (1048576, 25, 50), (1048576, 50, 100)):
+        xx = torch.rand(M, N, dtype=torch.float64, device="cuda", generator=g) - 0.5
+        w = torch.rand(N, K, dtype=torch.float64, device="cuda", generator=g) - 0.5
+        res = torch.empty(M, K, dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            opt_matmul_device(M, N, K, xx.data_ptr(), w.data_ptr(), res.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            opt_matmul_device(M, N, K, xx.data_ptr(), w.data_ptr(), res.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        xh, wh = xx[:8192].cpu().numpy(), w.cpu().numpy()
+        impl.opt_matmul(xh, wh)
+        t0 = time.perf_counter()
+        want = impl.opt_matmul(xh, wh)
+        cpu_s = time.perf_counter() - t0
+        err = float(np.abs(res[:8192].cpu().numpy() - want).max())
+        out["M=%d N=%d K=%d" % (M, N, K)] = {"gpu_ms": ms, "gpu_tflops": 2.0 * M * N * K / ms / 1e9,
+                                           "gpu_gbs": 8.0 * (M * N + N * K + M * K) / ms / 1e6,
+                                           "cpu_gflops": 2.0 * 8192 * N * K / cpu_s / 1e9, "max_abs_err_vs_cpu": err}
+        del xx, w, res
     return out
 
 

@@ -5,3 +5,4 @@ the benchmark and the multi-GPU (torch.distributed / NCCL) plumbing."""
 from ._lib import G4SError, Timings, lib  # noqa: F401
 from .csr import CSR, HashSpGEMM, OuterSpGEMM, bsr_from_citcoms_nodes, compute_flop, mkl, spmv_csr_f64  # noqa: F401
 from . import mv  # noqa: F401
+from .opt_matmul import opt_matmul  # noqa: F401

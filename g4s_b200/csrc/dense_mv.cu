@@ -2,14 +2,15 @@
 //
 // The reference passes a row-major-filled dim x dim buffer to column-major CBLAS calls; element (i,j) of the
 // matrix the BLAS sees is A[i + j*dim] (full storage) or A[i + j(j+1)/2], i <= j (packed-upper view of the
-// same buffer, dspmv).  Each routine is HBM-bound (dim^2 or dim^2/2 doubles read once or twice), built from
-// two deterministic primitives:
-//   row_part : thread per row i, coalesced along i for a fixed column j:  sum_{j in [jlo(i), jhi)} a(i,j) x[j]
-//   col_dot  : warp per column j, coalesced along the column:             sum_{i <  lim(j)} a(i,j) x[i]
-//   dgemv : C = row_part(all j)                         (mv/mv.c:23-27: ColMajor, NoTrans, alpha 1, beta 0)
-//   dsymv : C = row_part(j >= i) + col_dot(i < j)       (mv/mv.c:6-10 : ColMajor, Upper)
-//   dtrmv : B <- col_dot(i <= j)                        (mv/mv.c:12-15: ColMajor, Upper, Trans, NonUnit; in place)
+// same buffer, dspmv).  Each routine is HBM-bound and reads every stored element it needs exactly ONCE:
+//   dgemv : row_part — thread per row i, coalesced along i for a fixed column j: sum_j a(i,j) x[j]
+//                                                       (mv/mv.c:23-27: ColMajor, NoTrans, alpha 1, beta 0)
+//   dsymv : upper_tile — one pass over the upper triangle; element a(i,j), i <= j, feeds BOTH y[i] += a x[j] and (i < j)
+//           y[j] += a x[i]                              (mv/mv.c:6-10 : ColMajor, Upper)
+//   dtrmv : upper_tile, column sums only: B <- sum_{i <= j} a(i,j) B[i]
+//                                                       (mv/mv.c:12-15: ColMajor, Upper, Trans, NonUnit; in place)
 //   dspmv : dsymv on the packed view                    (mv/mv.c:17-21: the driver calls it matrix_multiply_sspmv)
+// All sums are taken in a fixed order (partial results per tile, reduced by a last kernel): deterministic, no atomics.
 #include <algorithm>
 
 #include "common.cuh"
@@ -59,6 +60,73 @@ __global__ void __launch_bounds__(256) col_dot_kernel(const double *__restrict__
     if (lane == 0) out[j] = acc;
 }
 
+// One pass over the upper triangle.  CTA = 8 warps = 256 rows [256 rb, +256) x one chunk of columns [jc0, jc1); lane = row.
+// Columns are taken 32 at a time: 32 coalesced loads a[c] = a(i, j0 + c) per lane, then
+//   rows   : racc += a[c] x[j0 + c]                       for j >= i   (kept in a register over the whole chunk)
+//   columns: v[c]  = a[c] x[i]  for i < j (i <= j for dtrmv), summed over the warp's 32 rows by a halving exchange
+//            (31 shuffles for 32 columns; lane c ends with column j0 + c), then over the CTA's 8 warps in shared memory.
+// part_row[chunk][i] and part_col[rb][j] are summed by reduce_sym_kernel.  Tiles below the diagonal are skipped.
+template <bool PACKED, bool ROWS, bool DIAG_IN_COLS>
+__global__ void __launch_bounds__(256) upper_tile_kernel(const double *__restrict__ A, const double *__restrict__ x,
+                                                         double *__restrict__ part_row, double *__restrict__ part_col,
+                                                         int dim, int jchunk) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int rb = blockIdx.x, chunk = blockIdx.y;
+    const int jc0 = chunk * jchunk, jc1 = min(dim, jc0 + jchunk);
+    if (jc1 <= rb * 256) return;  // wholly below the diagonal
+    __shared__ double cs[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = rb * 256 + threadIdx.x;
+    const bool row_ok = i < dim;
+    const double xi = row_ok ? __ldg(x + i) : 0.0;
+    double racc = 0.0;
+    for (int j0 = max(jc0, (rb * 256) & ~31); j0 < jc1; j0 += 32) {
+        double v[32];
+        const double xj = j0 + lane < jc1 ? __ldg(x + j0 + lane) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = j0 + c;
+            double a = 0.0;
+            if (row_ok && j < jc1 && i <= j) a = __ldg(A + col_offset(j, dim, PACKED) + i);
+            if (ROWS) racc = fma(a, __shfl_sync(FULL, xj, c), racc);
+            v[c] = (DIAG_IN_COLS || i < j) ? a * xi : 0.0;
+        }
+        // halving exchange: after the step with offset o a lane keeps the columns whose bit o equals its own
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int c = 0; c < o; ++c) {
+                const double send = up ? v[c] : v[c + o], keep = up ? v[c + o] : v[c];
+                v[c] = keep + __shfl_xor_sync(FULL, send, o);
+            }
+        }
+        // lane L now holds the sum over the warp's rows of column j0 + L (bits consumed high to low = its own index)
+        cs[warp][lane] = v[0];
+        __syncthreads();
+        if (warp == 0 && j0 + lane < jc1) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += cs[w][lane];
+            part_col[(size_t)rb * dim + j0 + lane] = t;
+        }
+        __syncthreads();
+    }
+    if (ROWS && row_ok) part_row[(size_t)chunk * dim + i] = racc;
+}
+
+// out[i] = sum_chunk part_row[chunk][i] + sum_rb part_col[rb][i]; entries no tile wrote are zero (the buffers are cleared)
+__global__ void reduce_sym_kernel(const double *__restrict__ part_row, const double *__restrict__ part_col,
+                                  double *__restrict__ out, int dim, int nchunks, int nrb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim) return;
+    double s = 0.0;
+    if (part_row)
+        for (int c = 0; c < nchunks; ++c) s += part_row[(size_t)c * dim + i];
+    for (int r = 0; r < nrb; ++r) s += part_col[(size_t)r * dim + i];
+    out[i] = s;
+}
+
 // out[i] = sum_c partial[c][i] (+ extra[i])
 __global__ void reduce_partials_kernel(const double *__restrict__ partial, const double *__restrict__ extra,
                                        double *__restrict__ out, int dim, int nchunks) {
@@ -89,22 +157,29 @@ int dense_mv_run(int op, const double *A, double *B, double *C, int dim, cudaStr
             reduce_partials_kernel<<<row_blocks, 256, 0, stream>>>(partial, nullptr, C, dim, nchunks);
             G4S_CHECK_LAUNCH("reduce_partials_kernel");
             break;
-        case 1:  // dsymv
-        case 3:  // dspmv
-            if (op == 1) row_part_kernel<true, false><<<grid, 256, 0, stream>>>(A, B, partial, dim, jchunk);
-            else row_part_kernel<true, true><<<grid, 256, 0, stream>>>(A, B, partial, dim, jchunk);
-            G4S_CHECK_LAUNCH("row_part_kernel");
-            if (op == 1) col_dot_kernel<false><<<col_blocks, 256, 0, stream>>>(A, B, tmp, dim, 0);
-            else col_dot_kernel<true><<<col_blocks, 256, 0, stream>>>(A, B, tmp, dim, 0);
-            G4S_CHECK_LAUNCH("col_dot_kernel");
-            reduce_partials_kernel<<<row_blocks, 256, 0, stream>>>(partial, tmp, C, dim, nchunks);
-            G4S_CHECK_LAUNCH("reduce_partials_kernel");
+        case 1:    // dsymv
+        case 3:    // dspmv
+        case 2: {  // dtrmv: B <- U^T B, through a temporary because every column reads the old B
+            const int nrb = row_blocks;
+            int sch = std::max(1, std::min((dim + 255) / 256, (sm_count() * 4 + nrb - 1) / nrb));
+            const int sj = (((dim + sch - 1) / sch) + 255) / 256 * 256;
+            sch = (dim + sj - 1) / sj;
+            double *prow = nullptr, *pcol = nullptr;
+            G4S_CUDA(cudaMallocAsync(&prow, sizeof(double) * (size_t)sch * dim, stream));
+            G4S_CUDA(cudaMallocAsync(&pcol, sizeof(double) * (size_t)nrb * dim, stream));
+            G4S_CUDA(cudaMemsetAsync(prow, 0, sizeof(double) * (size_t)sch * dim, stream));
+            G4S_CUDA(cudaMemsetAsync(pcol, 0, sizeof(double) * (size_t)nrb * dim, stream));
+            const dim3 sgrid(nrb, sch);
+            if (op == 1) upper_tile_kernel<false, true, false><<<sgrid, 256, 0, stream>>>(A, B, prow, pcol, dim, sj);
+            else if (op == 3) upper_tile_kernel<true, true, false><<<sgrid, 256, 0, stream>>>(A, B, prow, pcol, dim, sj);
+            else upper_tile_kernel<false, false, true><<<sgrid, 256, 0, stream>>>(A, B, nullptr, pcol, dim, sj);
+            G4S_CHECK_LAUNCH("upper_tile_kernel");
+            reduce_sym_kernel<<<row_blocks, 256, 0, stream>>>(op == 2 ? nullptr : prow, pcol, op == 2 ? B : C, dim, sch, nrb);
+            G4S_CHECK_LAUNCH("reduce_sym_kernel");
+            G4S_CUDA(cudaFreeAsync(prow, stream));
+            G4S_CUDA(cudaFreeAsync(pcol, stream));
             break;
-        case 2:  // dtrmv: B <- U^T B, through a temporary because every column reads the old B
-            col_dot_kernel<false><<<col_blocks, 256, 0, stream>>>(A, B, tmp, dim, 1);
-            G4S_CHECK_LAUNCH("col_dot_kernel");
-            G4S_CUDA(cudaMemcpyAsync(B, tmp, sizeof(double) * (size_t)dim, cudaMemcpyDeviceToDevice, stream));
-            break;
+        }
         default:
             cudaFreeAsync(partial, stream);
             cudaFreeAsync(tmp, stream);

@@ -350,6 +350,20 @@ void spmm_dense(uint32_t numNodes, uint32_t degree, const double **edgeWeight, c
 int g4s_ebe_matvec_device(int nel, int ndof, const double *elt_k_dev, const int *elem_dofs_dev, const double *u_dev,
                           double *Au_dev, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------------
+ * OptMatmul: the dense fp64 product DeePMD-kit routes through the G4S engine,
+ * res[M,K] = xx[M,N] w[N,K], all row-major (deepmd/source/op/opt_matmul.cc:24-62; engine loop
+ * deepmd/source/op/graph.h:21-32: one vertex per row of xx, degree K, gather = a dot product of length N), and the two
+ * products of its registered gradient (deepmd/source/op/_opt_matmul_grad.py): dxx[M,N] = grad[M,K] w^T,
+ * dw[N,K] = xx^T grad (either output may be NULL).  FP64 tensor cores (DMMA) on the GPU.  g4s_opt_matmul takes host
+ * pointers (what OptMatmulOp::Compute holds: tensor.flat<double>().data()) and copies inside the call.
+ * ---------------------------------------------------------------------------------------------------- */
+int g4s_opt_matmul_device(int M, int N, int K, const double *xx_dev, const double *w_dev, double *res_dev, void *stream);
+int g4s_opt_matmul_grad_device(int M, int N, int K, const double *xx_dev, const double *w_dev, const double *grad_dev,
+                               double *dxx_dev, double *dw_dev, void *stream);
+int g4s_opt_matmul(int M, int N, int K, const double *xx, const double *w, double *res);
+
 #ifdef __cplusplus
 }
 #endif

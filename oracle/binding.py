@@ -144,6 +144,15 @@ class Oracle:
         getattr(self.lib, "oracle_" + name)(_dp(A), _dp(B), _dp(Cv), C.c_int(dim))
         return B, Cv
 
+    def opt_matmul(self, xx, w):
+        """res = xx w as the engine computes it (deepmd/source/op/opt_matmul.cc:47-53 in graph.h:21-32)."""
+        xx, w = _f64(xx), _f64(w)
+        M, N = xx.shape
+        K = w.shape[1]
+        res = np.empty((M, K), dtype=np.float64)
+        self.lib.oracle_opt_matmul(C.c_int(M), C.c_int(N), C.c_int(K), _dp(xx), _dp(w), _dp(res))
+        return res
+
     def bsr_spmm(self, browptr, bcolids, bvalues, bs, Bd):
         browptr, bcolids, bvalues, Bd = _i32(browptr), _i32(bcolids), _f64(bvalues), _f64(Bd)
         mb = len(browptr) - 1
@@ -337,6 +346,15 @@ class Ref:
         r1, c1, v1, r2, c2, v2 = _i32(A[2]), _i32(A[3]), _f64(A[4]), _i32(B[2]), _i32(B[3]), _f64(B[4])
         return bool(self.lib.ref_csr_equal(C.c_int(A[0]), C.c_int(A[1]), C.c_int(len(c1)), _ip(r1), _ip(c1), _dp(v1),
                                            _ip(r2), _ip(c2), _dp(v2)))
+
+    def opt_matmul(self, xx, w):
+        """res = xx w through the reference's own GraphProcess (deepmd/source/op/graph.h, compiled where it lies)."""
+        xx, w = _f64(xx), _f64(w)
+        M, N = xx.shape
+        K = w.shape[1]
+        res = np.empty((M, K), dtype=np.float64)
+        self.lib.ref_opt_matmul(C.c_int(M), C.c_int(N), C.c_int(K), _dp(xx), _dp(w), _dp(res))
+        return res
 
     def dense_mv(self, name, A, B):
         """mv/mv.c's own matrix_multiply_{dsymv,dtrmv,sspmv,dgemv}(A,B,C,dim) on OpenBLAS."""

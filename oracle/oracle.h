@@ -34,6 +34,7 @@ void oracle_dspmv(const double *A, const double *B, double *C, int dim);
 int oracle_omp_max_threads(void);
 long long oracle_laplacian3d27_nnz(int n, long long row0, long long row1);
 void oracle_gen_laplacian3d27(int n, long long row0, long long row1, int *rowptr, int *colids, double *values);
+void oracle_opt_matmul(int M, int N, int K, const double *xx, const double *w, double *res);
 void oracle_bsr_spmm(int mb, int bs, const int *browptr, const int *bcolids, const double *bvalues, int ncol,
                      const double *B, double *C);
 

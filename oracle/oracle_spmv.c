@@ -195,3 +195,18 @@ void oracle_ebe_matvec(int nel, int ends, int dims, const double *elt_k, const i
             }
     }
 }
+
+/* OptMatmul: res[M,K] = xx[M,N] w[N,K], row-major, restating the gather of
+ * deepmd/source/op/opt_matmul.cc:47-53 inside the engine loop of deepmd/source/op/graph.h:21-32 — one vertex per row of
+ * xx, one gather per output column, "result[e*Col+a] = 0; for k: result[e*Col+a] += edgeWeight[e][k] * states[k*Col+a]"
+ * (k ascending, one product and one addition per term; -ffp-contract=off keeps them separate).  The reference pins the
+ * thread count to 8 with schedule(dynamic,1); the result does not depend on it.  Pinned against the reference's own
+ * GraphProcess (oracle/_ref, ref_opt_matmul) in tests/test_opt_matmul.py. */
+void oracle_opt_matmul(int M, int N, int K, const double *xx, const double *w, double *res) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int e = 0; e < M; ++e)
+        for (int a = 0; a < K; ++a) {
+            res[(size_t)e * K + a] = 0;
+            for (int k = 0; k < N; ++k) res[(size_t)e * K + a] += xx[(size_t)e * N + k] * w[(size_t)k * K + a];
+        }
+}

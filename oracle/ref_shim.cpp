@@ -177,3 +177,37 @@ int ref_csr_equal(int rows, int cols, int nnz, int *rpt1, int *col1, double *val
 }
 
 }  // extern "C"
+
+// ---- OptMatmul through the reference's own engine loop ------------------------------------------------------------------
+// deepmd/source/op/graph.h is included unmodified (GraphProcess, struct Graph); the TensorFlow op around it
+// (opt_matmul.cc) cannot be built here, so its gather lambda (opt_matmul.cc:47-53) is repeated below word for word except
+// for the captured Nsize, which is a global in the reference too.
+#include <omp.h>
+#include <stdio.h>
+
+#include <vector>
+namespace deepmd_ref {
+#include G4S_REF_DEEPMD_GRAPH_H  // -D from oracle/Makefile: $(REF)/deepmd/source/op/graph.h (mm/inc has a graph.h of its own)
+int Nsize;
+}  // namespace deepmd_ref
+extern "C" int ref_opt_matmul(int M, int N, int K, const double *xx, const double *w, double *result) {
+    using namespace deepmd_ref;
+    Graph graph;
+    Nsize = N;
+    graph.states = w;
+    graph.numNodes = M;
+    graph.degree = K;
+    std::vector<const double *> A((size_t)M);
+    for (int i = 0; i < M; i++) A[i] = xx + (size_t)i * N;
+    graph.edgeWeight = A.data();
+    GraphProcess(&graph, result,
+                 [&](int e, int a, struct Graph *graph, double *result) {
+                     int Col = getNeighbors(graph, e);
+                     result[e * Col + a] = 0;
+                     for (int k = 0; k < Nsize; k++) {
+                         result[e * Col + a] += graph->edgeWeight[e][k] * graph->states[k * Col + a];
+                     }
+                 },
+                 [&](int e, struct Graph *graph, double *Au) {});
+    return 0;
+}
