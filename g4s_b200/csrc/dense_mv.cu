@@ -161,9 +161,10 @@ int dense_mv_run(int op, const double *A, double *B, double *C, int dim, cudaStr
         case 3:    // dspmv
         case 2: {  // dtrmv: B <- U^T B, through a temporary because every column reads the old B
             const int nrb = row_blocks;
-            int sch = std::max(1, std::min((dim + 255) / 256, (sm_count() * 4 + nrb - 1) / nrb));
-            const int sj = (((dim + sch - 1) / sch) + 255) / 256 * 256;
-            sch = (dim + sj - 1) / sj;
+            // square 256 x 256 tiles (the triangle is then ~ nrb^2 / 2 CTAs of equal work, diagonal tiles half of it); for very
+            // large dim wider tiles keep the two partial buffers below ~64 chunks x dim doubles
+            const int sj = std::max(256, ((dim + 63) / 64 + 255) / 256 * 256);
+            const int sch = (dim + sj - 1) / sj;
             double *prow = nullptr, *pcol = nullptr;
             G4S_CUDA(cudaMallocAsync(&prow, sizeof(double) * (size_t)sch * dim, stream));
             G4S_CUDA(cudaMallocAsync(&pcol, sizeof(double) * (size_t)nrb * dim, stream));
