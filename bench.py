@@ -920,7 +920,10 @@ def bench_spgemm(g4s_b200, torch, args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     phases = (C.c_double * 4)()
+    g4s_b200.lib().g4s_spgemm_set_phase_timing(C.c_int(1))  # one more product with the per-phase events switched on
+    g4s_b200.HashSpGEMM(A, A).make_empty()
     g4s_b200.lib().g4s_spgemm_last_phase_ms(phases)
+    g4s_b200.lib().g4s_spgemm_set_phase_timing(C.c_int(0))
     nnza = A.nnz
     rows = A.rows
     nbytes = 2 * (12.0 * nnza + 4.0 * (rows + 1)) + 12.0 * nnzc + 4.0 * (rows + 1)
@@ -934,6 +937,11 @@ def bench_spgemm(g4s_b200, torch, args):
                        "rows": rows, "nnzA": nnza, "nnzC": nnzc, "flop": flop},
             "phase_ms": {"binning": phases[0], "symbolic": phases[1], "scan_alloc": phases[2], "numeric": phases[3]},
             "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "spgemm_merge_row_kernel<5,1> (numeric; every row of this product is in the "
+                         "merge class)", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": measured_peak()[0], "unit": "GB/s",
+                         "frac": nbytes / (ms * 1e-3) / 1e9 / measured_peak()[0],
+                         "note": "algorithmic bytes of the whole product (A + B + C, SURVEY.md 8d) over the whole product's "
+                                 "time (binning + symbolic + scan + numeric): conservative for the numeric kernel alone"},
             "e2e": {"value": flop / e2e_s / 1e9, "unit": "GFLOP/s", "seconds": e2e_s,
                     "h2d_bytes_per_step": 2 * (12 * nnza + 4 * (rows + 1)), "d2h_bytes_per_step": 12 * nnzc + 4 * (rows + 1),
                     "timings": {k: getattr(t, k) for k in ("create", "spmm", "export_csr", "destroy", "total")}}}

@@ -278,6 +278,15 @@ def OuterSpGEMM(a, b, stream=None):
     return CSR._from_handle(h)
 
 
+def HeapSpGEMM(a, b, stream=None):
+    """HeapSpGEMM (mm/inc/heap_mult.h:47-223): k-way heap merge of the sorted rows of b; same C as HashSpGEMM."""
+    if a.cols != b.rows:
+        raise ValueError("non-conformable operands")
+    h = C.c_void_p()
+    check(lib().g4s_spgemm_heap_device(a.handle, b.handle, C.byref(h), _stream_ptr(stream)))
+    return CSR._from_handle(h)
+
+
 def mkl(A, B, timing=None):
     """mkl(A, B, C, timing) (mm/inc/mkl_mult.h:113-117 -> :40-110): host CSR in, host CSR out, phases in timing."""
     a, b = A.to_host(), B.to_host()

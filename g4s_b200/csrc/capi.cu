@@ -312,6 +312,11 @@ int g4s_csr_destroy(g4s_csr_t h) {
     spmv_free_plan(h);
     if (h->owns && h->pooled) {
         cudaDeviceSynchronize();  // cudaFree's implicit guarantee: nothing in flight still uses the arrays
+        if (h->pool_base) {
+            cudaFreeAsync(h->pool_base, 0);
+            h->rowptr = h->colids = nullptr;
+            h->values = nullptr;
+        }
         if (h->rowptr) cudaFreeAsync(h->rowptr, 0);
         if (h->colids) cudaFreeAsync(h->colids, 0);
         if (h->values) cudaFreeAsync(h->values, 0);

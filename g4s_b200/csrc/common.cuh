@@ -33,6 +33,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     } while (0)
 
 int ensure_device();  // G4S_OK when the current device is usable (sm_100), else G4S_ERR_CUDA
+// stable LSD radix sort of (key, 8-byte value) pairs by the low end_bit bits; result in (k1, v1) (radix_sort.cu)
+int radix_sort_pairs_u64(unsigned long long *k0, unsigned long long *k1, unsigned long long *v0, unsigned long long *v1,
+                         long long n, int end_bit, cudaStream_t stream);
 int sm_count();
 
 // cudaFuncSetAttribute state is per device: a once-per-process flag would leave every kernel that needs > 48 KB of dynamic
@@ -95,6 +98,7 @@ struct g4s_csr {
     bool owns = false;
     int sorted_cols = -1;  // -1 unknown, 1 every row's column ids strictly ascending, 0 not (SpGEMM merge class)
     bool pooled = false;  // arrays came from cudaMallocAsync (stream-ordered pool) rather than cudaMalloc
+    void *pool_base = nullptr;  // pooled: the three arrays are slices of this one allocation (a repeated SpGEMM's result)
     g4s::SpmvPlan plan;
     // row-compressed blocks (off-diagonal part of a multi-GPU row block): local row r is row row_map[r] of a
     // block with full_rows rows

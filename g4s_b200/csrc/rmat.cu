@@ -12,7 +12,6 @@
 // The ordering step is a key-value radix sort from CUB (header-only, ships with the CUDA toolkit).  It runs
 // once per input in set-up code, outside every timed region; the measured hot paths (SpMV, SpGEMM) contain no
 // library kernels.
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 
@@ -118,12 +117,14 @@ int edges_to_csr(long long m, long n, const long *start, const long *end, const 
     G4S_CHECK_LAUNCH("pack_keys_kernel");
     int vbits = 1;
     while ((1L << vbits) < n) ++vbits;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    G4S_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, w, w1, m, 0, 32 + vbits, stream));
-    G4S_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    G4S_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, w, w1, m, 0, 32 + vbits, stream));
-    count_launch(8);
+    // the library's own stable radix sort (radix_sort.cu) ping-pongs between two pairs of buffers: the caller's weights are
+    // copied first, because the even passes write into the source pair
+    double *w0 = nullptr;
+    G4S_CUDA(cudaMalloc(&w0, sizeof(double) * (size_t)m));
+    G4S_CUDA(cudaMemcpyAsync(w0, w, sizeof(double) * (size_t)m, cudaMemcpyDeviceToDevice, stream));
+    if ((rc = radix_sort_pairs_u64(k0, k1, reinterpret_cast<unsigned long long *>(w0), reinterpret_cast<unsigned long long *>(w1), m,
+                                   32 + vbits, stream)))
+        return rc;
     int *head = nullptr, *idx = nullptr;
     G4S_CUDA(cudaMalloc(&head, sizeof(int) * ((size_t)m + 1)));
     G4S_CUDA(cudaMalloc(&idx, sizeof(int) * ((size_t)m + 1)));
@@ -138,7 +139,7 @@ int edges_to_csr(long long m, long n, const long *start, const long *end, const 
     cudaFree(k0);
     cudaFree(k1);
     cudaFree(w1);
-    cudaFree(tmp);
+    cudaFree(w0);
     cudaFree(head);
     cudaFree(idx);
     *out = h;

@@ -235,16 +235,16 @@ struct SpgemmArgs {
     int *row_nnz;
     const int *row_work;  // intermediate products per row (sizes the symbolic table)
     int sub_lg;  // lanes cooperating on one row of B (log2), chosen from B's mean row length
-    const int *go;  // null, or a device word: 0 = the launch parameters were a wrong guess, every kernel returns at once
+    const int *go;  // null, or a device word: non-zero = the launch parameters were a wrong guess, every kernel returns at once
 };
 #define G4S_SPGEMM_GUARD(a)                         \
     do {                                            \
-        if ((a).go && __ldg((a).go) == 0) return;   \
+        if ((a).go && __ldg((a).go) != 0) return;   \
     } while (0)
 
 // The host decisions of a product (rows per size class, nnz of C, ...) are launch parameters.  For a repeated product of
 // the same handles they are GUESSED from the previous call and checked on the device, so that the host never waits in the
-// middle of a product: `go` stays 1 when the freshly computed counters equal the guess.
+// middle of a product: `go` stays 0 when the freshly computed counters equal the guess.
 struct SpgemmGuessDev {
     int count[7];
     int max_work, merge_lists;
@@ -257,14 +257,14 @@ __global__ void spgemm_validate_bins_kernel(const int *__restrict__ dcount, cons
                                             const SpgemmGuessDev g, int nclass, int *__restrict__ go) {
     bool ok = *dtotal == g.total_work && dcount[2 * nclass] == g.max_work && dcount[4 * nclass + 1] == g.merge_lists;
     for (int c = 0; c < nclass; ++c) ok = ok && dcount[c] == g.count[c];
-    if (!ok) *go = 0;
+    if (!ok) *go = 1;
 }
 __global__ void spgemm_validate_nnz_kernel(const int *__restrict__ dcount2, const int *__restrict__ total,
                                            const SpgemmGuessDev g, int nclass, int *__restrict__ go) {
     bool ok = (long long)*total == g.cnnz;
     if (g.check_ncount)
         for (int c = 0; c < nclass; ++c) ok = ok && dcount2[c] == g.ncount[c];
-    if (!ok) *go = 0;
+    if (!ok) *go = 1;
 }
 
 template <int GROUP>
@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
 }
 
 static thread_local double t_phase_ms[4] = {0, 0, 0, 0};
+static thread_local bool t_want_phases = false;  // g4s_spgemm_set_phase_timing: four more event records per product
 
 template <int GROUP, int TABLE, int WMAX, int THREADS, bool NUMERIC>
 static int launch_smem(const SpgemmArgs &a, const int *list, int nlist, cudaStream_t stream) {
@@ -987,6 +988,7 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
 // Scratch reused across calls on the calling thread (row work, row lists, counters): SpGEMM is called in loops
 // (the reference's driver runs it 11 times, mm/src/mkl_spgemm.cpp:67-79) and cudaMalloc is a device-wide sync.
 struct Workspace {
+    static constexpr size_t CTL_BYTES = sizeof(unsigned long long) + sizeof(int) * (2 + 4 * NCLASS + 2);
     int device = -1;
     size_t rows_cap = 0;
     int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
@@ -1008,12 +1010,13 @@ struct Workspace {
             device = dev;
         }
         if (!dcount) {
-            G4S_CUDA(cudaMalloc(&dcount, sizeof(int) * (4 * NCLASS + 2)));
-            G4S_CUDA(cudaMalloc(&dtotal, sizeof(unsigned long long)));
+            // one control block, cleared by a single memset per product: total work | wrong-guess flag | class counters
+            G4S_CUDA(cudaMalloc(&dtotal, CTL_BYTES));
+            dgo = reinterpret_cast<int *>(dtotal + 1);
+            dcount = dgo + 2;
             G4S_CUDA(cudaMalloc(&spa_next, sizeof(int)));
             G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 2)));
             G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
-            G4S_CUDA(cudaMalloc(&dgo, sizeof(int)));
             G4S_CUDA(cudaMallocHost(&hgo, sizeof(int)));
             for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
         }
@@ -1128,8 +1131,8 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     if (allow_guess && B->sorted_cols >= 0)
         for (auto &gq : t_guess)
             if (gq.stamp && gq.matches(A, B, cur_dev)) guess = &gq;
-    G4S_CUDA(cudaMemsetAsync(ws.dgo, 1, sizeof(int), stream));
-    G4S_CUDA(cudaEventRecord(ws.ev[0], stream));
+    const bool phases = t_want_phases;
+    if (phases) G4S_CUDA(cudaEventRecord(ws.ev[0], stream));
 
     // ---- binning (BIN::set_max_bin) -------------------------------------------------------------------------
     Bins b;
@@ -1137,8 +1140,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     b.perm = ws.perm;
     int *row_nnz = ws.row_nnz;
     int *dcount = ws.dcount;
-    G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int) * (4 * NCLASS + 2), stream));
-    G4S_CUDA(cudaMemsetAsync(ws.dtotal, 0, sizeof(unsigned long long), stream));
+    G4S_CUDA(cudaMemsetAsync(ws.dtotal, 0, Workspace::CTL_BYTES, stream));
     const int threads = 256;
     const int blocks = (M + threads - 1) / threads;
     if (B->sorted_cols < 0) {  // once per matrix: are B's rows sorted? (decides whether class 1 may merge)
@@ -1190,7 +1192,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
         bin_fill_kernel<<<blocks, threads, 0, stream>>>(ws.row_class, M, dcount + NCLASS, b.perm, row_nnz);
         G4S_CHECK_LAUNCH("bin_fill_kernel");
     }
-    G4S_CUDA(cudaEventRecord(ws.ev[1], stream));
+    if (phases) G4S_CUDA(cudaEventRecord(ws.ev[1], stream));
 
     // lanes per row of B: next power of two >= B's mean row length
     int sub_lg = 0;
@@ -1236,7 +1238,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     // ---- symbolic ---------------------------------------------------------------------------------------------
     rc = run_phase(a, b, false, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
     if (rc) return rc;
-    G4S_CUDA(cudaEventRecord(ws.ev[2], stream));
+    if (phases) G4S_CUDA(cudaEventRecord(ws.ev[2], stream));
 
     // ---- row pointers (scan straight into C) + allocation of C's arrays from the stream-ordered pool --------------
     g4s_csr *C = new (std::nothrow) g4s_csr();
@@ -1245,7 +1247,17 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     C->cols = N;
     C->owns = true;
     C->pooled = true;
-    G4S_CUDA(cudaMallocAsync(&C->rowptr, sizeof(int) * ((size_t)M + 1) + 64, stream));
+    long long cnnz = guess ? guess->g.cnnz : 0;
+    if (guess) {  // nnz(C) is part of the guess: row pointers, column ids and values come from one allocation
+        const size_t b0 = (sizeof(int) * ((size_t)M + 1) + 64 + 255) & ~(size_t)255;
+        const size_t b1 = (sizeof(int) * (size_t)cnnz + 64 + 255) & ~(size_t)255;
+        G4S_CUDA(cudaMallocAsync(&C->pool_base, b0 + b1 + sizeof(double) * (size_t)cnnz + 64, stream));
+        C->rowptr = reinterpret_cast<int *>(C->pool_base);
+        C->colids = reinterpret_cast<int *>(reinterpret_cast<char *>(C->pool_base) + b0);
+        C->values = reinterpret_cast<double *>(reinterpret_cast<char *>(C->pool_base) + b0 + b1);
+    } else {
+        G4S_CUDA(cudaMallocAsync(&C->rowptr, sizeof(int) * ((size_t)M + 1) + 64, stream));
+    }
     // numeric classes (by nnz) are counted while the scan runs; both results come back with the scan's one sync
     int *dcount2 = dcount + 2 * NCLASS + 1;
     // rows of classes 1 and 2 never move; if one of them holds every row there is nothing to re-bin
@@ -1259,7 +1271,6 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
             G4S_CUDA(cudaMemcpyAsync(ws.hcount + 2 * NCLASS + 1, dcount2, sizeof(int) * NCLASS, cudaMemcpyDeviceToHost, stream));
         }
     }
-    long long cnnz = guess ? guess->g.cnnz : 0;
     rc = exclusive_scan_i32(row_nnz, C->rowptr, M, 1, guess ? nullptr : &cnnz, stream);
     if (rc == G4S_OK && guess) {
         SpgemmGuessDev gd = guess->g;
@@ -1273,9 +1284,11 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
         return rc;
     }
     C->nnz = cnnz;
-    G4S_CUDA(cudaMallocAsync(&C->colids, sizeof(int) * (size_t)cnnz + 64, stream));
-    G4S_CUDA(cudaMallocAsync(&C->values, sizeof(double) * (size_t)cnnz + 64, stream));
-    G4S_CUDA(cudaEventRecord(ws.ev[3], stream));
+    if (!guess) {
+        G4S_CUDA(cudaMallocAsync(&C->colids, sizeof(int) * (size_t)cnnz + 64, stream));
+        G4S_CUDA(cudaMallocAsync(&C->values, sizeof(double) * (size_t)cnnz + 64, stream));
+    }
+    if (phases) G4S_CUDA(cudaEventRecord(ws.ev[3], stream));
 
     // ---- numeric ----------------------------------------------------------------------------------------------
     a.crpt = C->rowptr;
@@ -1310,19 +1323,19 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
         g4s_csr_destroy(C);
         return rc;
     }
-    G4S_CUDA(cudaEventRecord(ws.ev[4], stream));
+    if (phases) G4S_CUDA(cudaEventRecord(ws.ev[4], stream));
     if (slab_keys) G4S_CUDA(cudaFreeAsync(slab_keys, stream));
     if (slab_vals) G4S_CUDA(cudaFreeAsync(slab_vals, stream));
     if (guess) G4S_CUDA(cudaMemcpyAsync(ws.hgo, ws.dgo, sizeof(int), cudaMemcpyDeviceToHost, stream));
     G4S_CUDA(cudaStreamSynchronize(stream));  // the product's one host wait
-    if (guess && *ws.hgo == 0) {  // the operands changed under the same handles: forget the guess, multiply again
+    if (guess && *ws.hgo != 0) {  // the operands changed under the same handles: forget the guess, multiply again
         guess->stamp = 0;
         g4s_csr_destroy(C);
         return spgemm_run_impl(A, B, Cout, stream, false);
     }
     for (int i = 0; i < 4; ++i) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, ws.ev[i], ws.ev[i + 1]);
+        if (phases) cudaEventElapsedTime(&ms, ws.ev[i], ws.ev[i + 1]);
         t_phase_ms[i] = ms;
     }
     if (!guess && guess_enabled()) {  // remember this product's decisions (least recently used slot)
@@ -1376,6 +1389,11 @@ int g4s_spgemm_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
     return spgemm_run(A, B, C, (cudaStream_t)stream);
+}
+
+int g4s_spgemm_set_phase_timing(int on) {
+    t_want_phases = on != 0;
+    return G4S_OK;
 }
 
 int g4s_spgemm_last_phase_ms(double *ms4) {

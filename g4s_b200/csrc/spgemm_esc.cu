@@ -9,7 +9,6 @@
 // than the hash path on every input measured (profiles/), and it needs 32 bytes of scratch per product; it exists for
 // the reference's algorithm inventory and as a device-side cross-check of the hash kernels.
 // The sort is CUB's DeviceRadixSort (library code, as in rmat.cu); expansion, compress and row pointers are ours.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -147,11 +146,14 @@ int spgemm_esc_run(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t stream) 
         count_launch();
         int rbits = 1;
         while ((1LL << rbits) < M) ++rbits;
-        size_t tmp_bytes = 0;
-        ESC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + rbits, stream));
-        ESC_CUDA(cudaMallocAsync(&tmp, tmp_bytes, stream));
-        ESC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, n, 0, 32 + rbits, stream));
-        count_launch();
+        // the library's own stable LSD radix sort (radix_sort.cu): (row << 32 | col) keys, values ride along
+        rc = radix_sort_pairs_u64(k0, k1, reinterpret_cast<unsigned long long *>(v0), reinterpret_cast<unsigned long long *>(v1), n,
+                                  32 + rbits, stream);
+        if (rc) {
+            release();
+            g4s_csr_destroy(C);
+            return rc;
+        }
         ESC_CUDA(cudaMallocAsync(&head, sizeof(int) * (size_t)n, stream));
         ESC_CUDA(cudaMallocAsync(&slot, sizeof(int) * (size_t)n, stream));
         const int nblocks = (int)((n + 255) / 256);

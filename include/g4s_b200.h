@@ -142,12 +142,18 @@ int g4s_spgemm_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
 /* Per-phase device milliseconds of the last g4s_spgemm_device on this thread: binning, symbolic, scan+alloc,
  * numeric(+sort). */
 int g4s_spgemm_last_phase_ms(double *ms4);
+/* phase timing costs five event records per product and is off by default: switch it on for the products you want reported */
+int g4s_spgemm_set_phase_timing(int on);
 /* The same product by expand - sort - compress, the GPU form of the reference's OuterSpGEMM "join"
  * (mm/inc/outer_mult.h:271-542: (row, col, value) triples, radix sort on (row << 32) | col, equal keys summed).  Same CSR
  * as g4s_spgemm_device; the values are summed in the reference's sequential order for EVERY row (bit-identical to
  * HashSpGEMM<false,true>).  Slower and 32 bytes of scratch per intermediate product (at most 2^31-1 of them): the
  * library's second, independent SpGEMM, for cross-checks and for the reference's algorithm inventory. */
 int g4s_spgemm_esc_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
+/* HeapSpGEMM (mm/inc/heap_mult.h:47-223): C = A B by a k-way heap merge of the sorted rows of B, rows of A of any length;
+ * same sorted CSR, values bit-identical to HashSpGEMM<false,true> (ties on a column leave the heap in A's stored order).
+ * G4S_ERR_INVALID when a row of B is not sorted by column. */
+int g4s_spgemm_heap_device(g4s_csr_t A, g4s_csr_t B, g4s_csr_t *C, void *stream);
 
 /* compute_flop / get_flop (mm/inc/mkl_mult.h:8-38, hash_mult.h:45-62): intermediate products, 64-bit.
  * row_work_dev may be NULL; else int32[rows] on the device (BIN::set_intprod_num, BIN.h:77-95). */
@@ -350,6 +356,13 @@ void spmm_dense(uint32_t numNodes, uint32_t degree, const double **edgeWeight, c
 int g4s_ebe_matvec_device(int nel, int ndof, const double *elt_k_dev, const int *elem_dofs_dev, const double *u_dev,
                           double *Au_dev, void *stream);
 
+
+/* Stable radix sort of n (64-bit key, 8-byte value) pairs by the low key_bits bits of the key, on the device, in place
+ * (the *_tmp arrays are scratch of the same size).  The library's own sort: counterpart of radix_sort(begin, end, buf, key)
+ * (mm/inc/radix_sort.h:701-705) as the join SpGEMM calls it (mm/inc/outer_mult.h:427-442); g4s_spgemm_esc_device and
+ * g4s_csr_from_edges_device sort with it. */
+int g4s_radix_sort_pairs_device(unsigned long long *keys_dev, unsigned long long *keys_tmp_dev, void *values_dev,
+                                void *values_tmp_dev, long long n, int key_bits, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * OptMatmul: the dense fp64 product DeePMD-kit routes through the G4S engine,

@@ -357,3 +357,28 @@ def test_dev_size_config5_bsr_closed_form(g4s):
     torch.cuda.synchronize()
     assert float((C2 - want).abs().max()) <= 1e-12 * (29.0 + 1.3 * 26)
     plan.destroy()
+
+
+# ---------------------------------------------------------------- the library's own radix sort -----------------------------
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 5), (4096, 12), (4097, 40), (300000, 57), (1 << 20, 64)])
+def test_radix_sort_pairs_is_a_stable_sort(g4s, n, bits):
+    """g4s_radix_sort_pairs_device against numpy's stable argsort: keys with many duplicates, values = input position, so any
+    pair of equal keys that changed order shows (mm/inc/radix_sort.h:701-705 is the reference's counterpart; the join
+    SpGEMM sums the values of equal keys left to right and needs the stability)."""
+    import torch
+
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, min(hi, 1 << 62), n, dtype=np.uint64, endpoint=True)
+    keys[rng.integers(0, n, n // 2)] = keys[0]                      # lots of duplicates
+    keys &= np.uint64(hi)
+    vals = np.arange(n, dtype=np.uint64)
+    k = torch.from_numpy(keys.view(np.int64)).cuda()
+    v = torch.from_numpy(vals.view(np.int64)).cuda()
+    kt, vt = torch.empty_like(k), torch.empty_like(v)
+    g4s._lib.check(g4s.lib().g4s_radix_sort_pairs_device(C.c_void_p(k.data_ptr()), C.c_void_p(kt.data_ptr()), C.c_void_p(v.data_ptr()),
+                                                        C.c_void_p(vt.data_ptr()), C.c_longlong(n), C.c_int(bits), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(k.cpu().numpy().view(np.uint64), keys[order])
+    np.testing.assert_array_equal(v.cpu().numpy().view(np.uint64), vals[order])

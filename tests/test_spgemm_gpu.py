@@ -118,6 +118,34 @@ def test_outer_spgemm_is_bit_exact(g4s, oracle, name):
     np.testing.assert_array_equal(C.values, val)
 
 
+def sorted_rows(t):
+    rp, ci, va = t[2], t[3].copy(), t[4].copy()
+    for r in range(t[0]):
+        s, e = rp[r], rp[r + 1]
+        o = np.argsort(ci[s:e], kind="stable")
+        ci[s:e], va[s:e] = ci[s:e][o], va[s:e][o]
+    return (t[0], t[1], rp, ci, va)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_heap_spgemm_is_bit_exact(g4s, oracle, name):
+    """HeapSpGEMM (mm/inc/heap_mult.h:47-223), the general k-way heap merge: any number of lists per row (the power-law
+    cases have rows of A with hundreds of entries), ties on a column leave the heap in A's stored order, so pattern AND
+    values equal HashSpGEMM<false,true>'s bit for bit.  B's rows must be sorted: the shuffled cases are sorted first (A
+    keeps its shuffled order — the merge does not care) and an unsorted B is refused."""
+    A, B, _, _, _, _ = case_with_oracle(oracle, name)
+    Bs = sorted_rows(B)
+    rpt, col, val = oracle.hash_spgemm(A, Bs)
+    C = g4s.HeapSpGEMM(as_csr(g4s, A), as_csr(g4s, Bs)).to_host()
+    assert (C.rows, C.cols) == (A[0], B[1])
+    np.testing.assert_array_equal(C.rowptr, rpt)
+    np.testing.assert_array_equal(C.colids, col)
+    np.testing.assert_array_equal(C.values, val)
+    if any(np.any(np.diff(B[3][B[2][r]:B[2][r + 1]]) <= 0) for r in range(B[0])):
+        with pytest.raises(g4s.G4SError):
+            g4s.HeapSpGEMM(as_csr(g4s, A), as_csr(g4s, B))
+
+
 def test_class6_global_hash_tables_still_match(g4s, oracle, monkeypatch):
     """Class 6 has two kernels: the dense accumulator (products with at most 2^20 columns) and hash tables in global
     memory (anything wider).  The wide case is too big for a parity test, so the hash kernel is forced on a small one."""

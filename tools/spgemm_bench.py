@@ -25,6 +25,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 ph = (C.c_double * 4)()
-g4s_b200.lib().g4s_spgemm_last_phase_ms(ph)
+g4s_b200.lib().g4s_spgemm_last_phase_ms(ph)  # zeros unless g4s_spgemm_set_phase_timing(1) was called
 print("n=%d rows=%d nnzA=%d nnzC=%d  %.3f ms  %.1f GFLOP/s  phases(ms): bin %.3f sym %.3f scan+alloc %.3f num %.3f"
       % (n, A.rows, A.nnz, nnzc, ms, flop / ms / 1e6, ph[0], ph[1], ph[2], ph[3]))

@@ -23,7 +23,7 @@ def run(name, A, reps=3):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     ph = (C.c_double * 4)()
-    g4s_b200.lib().g4s_spgemm_last_phase_ms(ph)
+    g4s_b200.lib().g4s_spgemm_last_phase_ms(ph)  # zeros unless g4s_spgemm_set_phase_timing(1) was called
     print("%-12s rows=%d nnzA=%d intprod=%.3g nnzC=%d : %.3f ms %.1f GFLOP/s  (bin %.3f sym %.3f scan %.3f num %.3f)"
           % (name, A.rows, A.nnz, flop / 2, nnzc, ms, flop / ms / 1e6, ph[0], ph[1], ph[2], ph[3]), flush=True)
 
