@@ -525,6 +525,10 @@ def run_ours(args, rank, world):
             except Exception:
                 ref = None
             line["spgemm"]["cpu_baseline"] = cpu_spgemm(ref, oracle, SPGEMM_GRID)
+            try:
+                line["spgemm"]["other_inputs"] = bench_spgemm_other(g4s_b200, torch)
+            except Exception as e:
+                line["spgemm"]["other_inputs"] = {"error": str(e)[:200]}
         if not args.no_other:
             try:
                 line["other_configs"] = bench_other_configs(g4s_b200, torch, peak)
@@ -832,6 +836,44 @@ def bench_opt_matmul(g4s_b200, torch):
                                            "gpu_gbs": 8.0 * (M * N + N * K + M * K) / ms / 1e6,
                                            "cpu_gflops": 2.0 * 8192 * N * K / cpu_s / 1e9, "max_abs_err_vs_cpu": err}
         del xx, w, res
+    return out
+
+
+def bench_spgemm_other(g4s_b200, torch):
+    """The hash / dense-accumulator size classes of g4s_spgemm_device on inputs where they carry the work (VERDICT r01 item 4;
+    configs[3] runs entirely in the merge class): A*A on the 3-D 27-point Laplacian n = 100 (705 M products, rows of 125
+    distinct columns: warp-per-row tables) and on R-MAT scale 16 (power-law rows: CTA tables and the dense accumulator).
+    Device-timed (3 warm-ups, 5 products), phases from one more product with the phase events on."""
+    import ctypes as C
+
+    L = g4s_b200.lib()
+    out = {}
+    for key, make in (("A*A 3-D 27-point n=100", lambda: g4s_b200.CSR.laplacian3d27(100)),
+                      ("A*A R-MAT scale 16 ef 16", lambda: g4s_b200.CSR.rmat(16, 16, seed=20240601))):
+        A = make()
+        flop = 2.0 * g4s_b200.compute_flop(A, A)
+        for _ in range(3):
+            g4s_b200.HashSpGEMM(A, A).make_empty()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            Cm = g4s_b200.HashSpGEMM(A, A)
+            nnzc = Cm.nnz
+            Cm.make_empty()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        ph = (C.c_double * 4)()
+        L.g4s_spgemm_set_phase_timing(C.c_int(1))
+        g4s_b200.HashSpGEMM(A, A).make_empty()
+        L.g4s_spgemm_last_phase_ms(ph)
+        L.g4s_spgemm_set_phase_timing(C.c_int(0))
+        nbytes = 2 * (12.0 * A.nnz + 4.0 * (A.rows + 1)) + 12.0 * nnzc + 4.0 * (A.rows + 1)
+        out[key] = {"rows": A.rows, "nnzA": A.nnz, "nnzC": nnzc, "ms": ms, "gflops": flop / ms / 1e6,
+                    "algorithmic_gbs": nbytes / ms / 1e6,
+                    "phase_ms": {"binning": ph[0], "symbolic": ph[1], "scan_alloc": ph[2], "numeric": ph[3]}}
+        A.make_empty()
     return out
 
 

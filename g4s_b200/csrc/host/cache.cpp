@@ -162,6 +162,12 @@ int g4s_csr_read_binary(const char *path, int *rows, int *cols, int *nnz, int **
     }
     bool sane = rp[0] == 0 && rp[h.rows] == (int)h.nnz;
     for (int64_t i = 0; sane && i < h.rows; ++i) sane = rp[i] <= rp[i + 1];
+    if (sane) {  // a stale, foreign or crafted file must not hand out-of-range columns to the GPU kernels
+        int bad = 0;
+#pragma omp parallel for reduction(| : bad) schedule(static)
+        for (int64_t k = 0; k < h.nnz; ++k) bad |= (ci[k] < 0) | (ci[k] >= (int)h.cols);
+        sane = bad == 0;
+    }
     if (sane && checksum_of((int)h.rows, h.nnz, rp, ci, va) != h.checksum) sane = false;
     if (!sane) {
         drop();
@@ -184,8 +190,12 @@ int g4s_csr_read_cached(const char *mtx_path, int *rows, int *cols, int *nnz, in
     const std::string cache = std::string(mtx_path) + ".g4scsr";
     struct stat sm, sc;
     const bool have_mtx = stat(mtx_path, &sm) == 0;
-    // a cache older than its text file is stale; a cache without a text file is used as it is
-    if (stat(cache.c_str(), &sc) == 0 && (!have_mtx || sc.st_mtime >= sm.st_mtime)) {
+    // a cache older than its text file is stale (compared at the file system's nanosecond resolution: a text file rewritten
+    // within the same second as its cache must not keep it); a cache without a text file is used as it is
+    auto not_older = [](const struct stat &c, const struct stat &m) {
+        return c.st_mtim.tv_sec > m.st_mtim.tv_sec || (c.st_mtim.tv_sec == m.st_mtim.tv_sec && c.st_mtim.tv_nsec >= m.st_mtim.tv_nsec);
+    };
+    if (stat(cache.c_str(), &sc) == 0 && (!have_mtx || not_older(sc, sm))) {
         if (g4s_csr_read_binary(cache.c_str(), rows, cols, nnz, rowptr, colids, values) == G4S_OK) {
             if (cache_hit) *cache_hit = 1;
             return G4S_OK;

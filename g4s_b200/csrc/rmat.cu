@@ -132,6 +132,8 @@ int edges_to_csr(long long m, long n, const long *start, const long *end, const 
     G4S_CHECK_LAUNCH("head_flags_kernel");
     long long unique = 0;
     if ((rc = exclusive_scan_i32(head, idx, m, 0, &unique, stream))) return rc;
+    if (unique > 2147483647LL || n > 2147483647L)
+        return fail(G4S_ERR_INVALID, "edge list: more than 2^31-1 distinct edges or vertices (int32 CSR)");
     if ((rc = alloc_csr(&h, (int)n, (int)n, unique))) return rc;
     merge_edges_kernel<<<grid, 256, 0, stream>>>(k1, w1, head, idx, m, (int)n, (int)unique, h->rowptr, h->colids, h->values);
     G4S_CHECK_LAUNCH("merge_edges_kernel");

@@ -1455,6 +1455,7 @@ int g4s_mkl_alloc(const int *arpt, const int *acol, const double *aval, const in
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     g4s_timings local;
+    g4s_timings_init(&local);  // timing == NULL: the flags below are read from an initialised struct
     g4s_timings *t = timing ? timing : &local;
     const unsigned char ms = t->measure_separate, mt = t->measure_total;
     g4s_timings_init(t);

@@ -313,6 +313,11 @@ struct XParts {
     unsigned long long *pool_counter;
     unsigned long long pool_base;
     int pool_n;
+    // how long a kernel waits for a peer's flag before it gives up (nanoseconds).  The flag is published by the peer's own
+    // product kernel, so the wait covers everything that can delay a peer's launch (plan building on its first product, host
+    // I/O between iterations, a debugger): the default is 10 minutes, G4S_PEER_TIMEOUT_S changes it.  Expiry traps — a peer
+    // that never launches would otherwise hang every rank silently.
+    unsigned long long wait_ns;
 };
 __device__ __forceinline__ double load_x_part(const XParts &xp, int c) {
     if (c >= xp.lo && c < xp.hi) return __ldg(xp.self_base + (c - xp.lo));  // own slice: the common case
@@ -345,8 +350,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// warp-collective: lane q waits until rank q has published this product's epoch.  Ten seconds without progress
-// means a peer died: trap, so that the failure is loud instead of a silent hang.
+// warp-collective: lane q waits until rank q has published this product's epoch.  xp.wait_ns (default 10 minutes) without
+// progress means a peer died: trap, so that the failure is loud instead of a silent hang.
 __device__ __forceinline__ void wait_peers(const XParts &xp, int lane) {
     if (lane < xp.world && ((xp.owner_mask >> lane) & 1u)) {
         unsigned long long t0;
@@ -354,7 +359,7 @@ __device__ __forceinline__ void wait_peers(const XParts &xp, int lane) {
         while (ld_acquire_sys_u64(xp.flags + lane) < xp.epoch) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 10000000000ULL) __trap();
+            if (t1 - t0 > xp.wait_ns) __trap();
             __nanosleep(200);
         }
     }
@@ -620,7 +625,7 @@ __global__ void __launch_bounds__(WARPS * 32) spmv_chunk_kernel(const SpmvArgs a
                     do {
                         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(xp.halo_done) : "memory");
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 10000000000ULL) __trap();
+                        if (t1 - t0 > xp.wait_ns) __trap();
                     } while (seen < xp.halo_target);
                 }
                 __syncwarp();
@@ -781,6 +786,7 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     none.pool_counter = nullptr;
     none.pool_base = 0;
     none.pool_n = 0;
+    none.wait_ns = 0;
     if (parts) kp<<<grid, WARPS * 32, smem, stream>>>(args, *parts);
     else if (accum) k1<<<grid, WARPS * 32, smem, stream>>>(args, none);
     else k0<<<grid, WARPS * 32, smem, stream>>>(args, none);
@@ -1072,6 +1078,12 @@ int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x
     xp.pool_counter = nullptr;
     xp.pool_base = 0;
     xp.pool_n = 0;
+    static const unsigned long long wait_ns = [] {
+        const char *e = getenv("G4S_PEER_TIMEOUT_S");
+        const double sec = e ? atof(e) : 600.0;
+        return (unsigned long long)((sec > 0 ? sec : 600.0) * 1e9);
+    }();
+    xp.wait_ns = wait_ns;
     if (p.part_colids) {
         const long long want = ((long long)p.nchunks + 8) / 9;  // grid of the 1 x 9 x 2 shape (launch_chunk_kernel)
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 2));
