@@ -75,20 +75,26 @@ __global__ void __launch_bounds__(256) upper_tile_kernel(const double *__restric
     const int jc0 = chunk * jchunk, jc1 = min(dim, jc0 + jchunk);
     if (jc1 <= rb * 256) return;  // wholly below the diagonal
     __shared__ double cs[8][32];
+    __shared__ double xs[256];  // x over the tile's columns (tiles are 256 wide unless dim is huge: then the tail reads global)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ROWS) {
+        if (jc0 + (int)threadIdx.x < jc1) xs[threadIdx.x] = __ldg(x + jc0 + threadIdx.x);
+        __syncthreads();
+    }
     const int i = rb * 256 + threadIdx.x;
     const bool row_ok = i < dim;
     const double xi = row_ok ? __ldg(x + i) : 0.0;
     double racc = 0.0;
     for (int j0 = max(jc0, (rb * 256) & ~31); j0 < jc1; j0 += 32) {
         double v[32];
-        const double xj = j0 + lane < jc1 ? __ldg(x + j0 + lane) : 0.0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             const int j = j0 + c;
             double a = 0.0;
             if (row_ok && j < jc1 && i <= j) a = __ldg(A + col_offset(j, dim, PACKED) + i);
-            if (ROWS) racc = fma(a, __shfl_sync(FULL, xj, c), racc);
+            // x[j] is the same for the whole warp: a shared-memory broadcast (a shuffle per column made dsymv 70 % slower than
+            // dtrmv, which needs none)
+            if (ROWS && j < jc1) racc = fma(a, j - jc0 < 256 ? xs[j - jc0] : __ldg(x + j), racc);
             v[c] = (DIAG_IN_COLS || i < j) ? a * xi : 0.0;
         }
         // halving exchange: after the step with offset o a lane keeps the columns whose bit o equals its own

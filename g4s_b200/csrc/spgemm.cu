@@ -91,8 +91,14 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
         bmaxlen = 0;
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    unsigned long long s = 0;  // this thread's share of the total work, over all the row blocks its CTA walks
+    // grid-stride over blocks of blockDim.x rows: the counters are folded in shared memory and hit global memory with ONE set
+    // of atomics per CTA at the end (one set per 256 rows — 65 K same-address atomics on configs[3] — was most of this
+    // kernel's 74 us)
+    const int nblk = (M + (int)blockDim.x - 1) / (int)blockDim.x;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int i = blk * blockDim.x + threadIdx.x;
     long long w = 0;
     int as = 0, ae = 0;
     if (i < M) {
@@ -134,7 +140,7 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
                 any = true;
                 if (threadIdx.x == 0) big_sum = 0;
                 __syncthreads();
-                const int row = blockIdx.x * blockDim.x + t;
+                const int row = blk * blockDim.x + t;
                 const int rs = __ldg(arpt + row), re = __ldg(arpt + row + 1);
                 long long part = 0;
                 for (int j = rs + threadIdx.x; j < re; j += blockDim.x) {
@@ -166,7 +172,8 @@ __global__ void row_work_kernel(const int *__restrict__ arpt, const int *__restr
             if (cls == 1 && alen > bmaxlen) atomicMax(&bmaxlen, alen);
         }
     }
-    unsigned long long s = (unsigned long long)w;
+    s += (unsigned long long)w;
+    }  // row blocks
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(&bsum, s);
@@ -566,16 +573,32 @@ __global__ void __launch_bounds__(THREADS) spgemm_thread_row_kernel(const Spgemm
 // smallest head column and folds every list that carries it, in list order — which is the reference's
 // accumulation order (j ascending over A's row, one entry of B's row per column; hash_mult.h:579-600), so the
 // values are bit-identical to HashSpGEMM<false,true> and the columns come out sorted with no sort at all.
-constexpr int MERGE_STAGE = 16;  // output entries per row staged in shared memory for the coalesced store
+constexpr int MERGE_STAGE_MAX = 16;  // output entries per row staged in shared memory for the coalesced store
 // K = lists per thread: the compare / fold code is unrolled per list, so rows of A with at most 5 entries (2-D 5-point
 // stencils) run a K = 5 instance (binning reports the longest class-1 row).
-template <int K, bool NUMERIC>
-__global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
-                                                               int nlist) {
+// FUSED (symbolic phase of a product whose every row is in this class — configs[3] — on the repeated-product path): the
+// kernel also does the binning pass's job for its rows.  It reads a row's entries of A and the extents of the rows of B they
+// select anyway, so the row's intermediate products, its class and the class / work counters (what row_work_kernel computes,
+// BIN::set_intprod_num + set_bin_id) cost a few integer operations instead of a second sweep over A (74 of 700 us);
+// spgemm_validate_bins_kernel then compares the counters with the guessed launch parameters as usual, and a row that does
+// not belong here (another class, or more lists than K) raises the wrong-guess flag directly.
+struct MergeFused {
+    int *class_count;            // the control block's counters (same layout as row_work_kernel's)
+    unsigned long long *total;
+    int *bad;
+};
+template <int K, bool NUMERIC, bool FUSED = false>
+__global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
+                                                               int nlist, const MergeFused fz = MergeFused()) {
     G4S_SPGEMM_GUARD(a);
     constexpr int THREADS = 256;
+    unsigned long long f_sum = 0;
+    int f_max = 0, f_len = 0, f_rows = 0;
     // numeric phase: [MERGE_STAGE][THREADS] columns and values; entry e of lane L sits in column (L + e) & 31 of its
     // warp's 32 columns, so that both the per-thread writes and the warp's read-back are bank-conflict-free
+    // (13 staged entries per row for the 5-list instance — 40 KB per CTA, a fifth CTA per SM at 46 registers — was measured:
+    // numeric 0.43 -> 0.55 ms on configs[3]; the register cap costs more than the extra warps give)
+    constexpr int MERGE_STAGE = MERGE_STAGE_MAX;
     __shared__ int s_col[NUMERIC ? MERGE_STAGE * THREADS : 1];
     __shared__ double s_val[NUMERIC ? MERGE_STAGE * THREADS : 1];
     const int t = threadIdx.x, lane = t & 31, tw = t - lane;
@@ -602,6 +625,17 @@ __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs 
                 end[u] = __ldg(a.brpt + k + 1);
                 if (pos[u] < end[u]) head[u] = __ldg(a.bcol + pos[u]);
             }
+        }
+        if (FUSED && active) {
+            long long w = 0;
+#pragma unroll
+            for (int u = 0; u < K; ++u) w += end[u] - pos[u];
+            const int wi = w > 2147483647LL ? 2147483647 : (int)w;
+            if (na > K || work_class(wi, a.N, na, true) != 1) *fz.bad = 1;  // not a row of this class: the guess was wrong
+            f_sum += (unsigned long long)w;
+            f_max = max(f_max, wi);
+            f_len = max(f_len, na);
+            ++f_rows;
         }
         int out = 0, nrow = 0;
         bool staged = false;
@@ -672,6 +706,38 @@ __global__ void __launch_bounds__(256) spgemm_merge_row_kernel(const SpgemmArgs 
                 }
             }
             __syncwarp();
+        }
+    }
+    if (FUSED) {  // one set of atomics per CTA (same-address atomics serialise: one set per warp cost 50-100 us)
+        __shared__ unsigned long long r_sum[THREADS / 32];
+        __shared__ int r_max[THREADS / 32], r_len[THREADS / 32], r_rows[THREADS / 32];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            f_sum += __shfl_xor_sync(0xffffffffu, f_sum, o);
+            f_max = max(f_max, __shfl_xor_sync(0xffffffffu, f_max, o));
+            f_len = max(f_len, __shfl_xor_sync(0xffffffffu, f_len, o));
+            f_rows += __shfl_xor_sync(0xffffffffu, f_rows, o);
+        }
+        if (lane == 0) {
+            r_sum[t >> 5] = f_sum;
+            r_max[t >> 5] = f_max;
+            r_len[t >> 5] = f_len;
+            r_rows[t >> 5] = f_rows;
+        }
+        __syncthreads();
+        if (t == 0) {
+            for (int w = 1; w < THREADS / 32; ++w) {
+                f_sum += r_sum[w];
+                f_max = max(f_max, r_max[w]);
+                f_len = max(f_len, r_len[w]);
+                f_rows += r_rows[w];
+            }
+            if (f_rows) {
+                atomicAdd(fz.total, f_sum);
+                atomicAdd(&fz.class_count[1], f_rows);
+                atomicMax(&fz.class_count[2 * NCLASS], f_max);
+                atomicMax(&fz.class_count[4 * NCLASS + 1], f_len);
+            }
         }
     }
 }
@@ -938,6 +1004,8 @@ struct Bins {
     long long total_work = 0;
     int max_work = 0;
     int merge_lists = MERGE_MAX_A;  // longest row of A in class 1
+    bool fused = false;             // symbolic merge kernel also bins (repeated all-merge-class product)
+    MergeFused fz = MergeFused();
 };
 
 static bool use_spa(int cols);
@@ -953,6 +1021,10 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
         const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
         if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else if (b.fused && k5)
+            spgemm_merge_row_kernel<5, false, true><<<std::min(grid, sm_count() * 8), 256, 0, stream>>>(a, list(1), b.count[1], b.fz);
+        else if (b.fused)
+            spgemm_merge_row_kernel<MERGE_MAX_A, false, true><<<std::min(grid, sm_count() * 8), 256, 0, stream>>>(a, list(1), b.count[1], b.fz);
         else if (k5) spgemm_merge_row_kernel<5, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else spgemm_merge_row_kernel<MERGE_MAX_A, false><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         G4S_CHECK_LAUNCH("spgemm_merge_row_kernel");
@@ -1155,14 +1227,18 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
         B->sorted_cols = ws.hcount[0] ? 0 : 1;
         G4S_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int), stream));
     }
-    if (M > 0) {
-        row_work_kernel<<<blocks, threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, ws.dtotal, dcount,
+    // every row in the merge class (configs[3]) on the repeated path: the symbolic kernel bins its own rows (MergeFused)
+    const bool fused_bin = guess && M > 0 && guess->g.count[1] == M && B->sorted_cols == 1;
+    if (M > 0 && !fused_bin) {
+        row_work_kernel<<<std::min(blocks, sm_count() * 8), threads, 0, stream>>>(A->rowptr, A->colids, B->rowptr, M, N, b.row_work, ws.dtotal, dcount,
                                                        ws.row_class, B->sorted_cols == 1);
         G4S_CHECK_LAUNCH("row_work_kernel");
     }
     if (guess) {  // launch with the previous product's numbers; the device checks them against the fresh counters
-        spgemm_validate_bins_kernel<<<1, 1, 0, stream>>>(dcount, ws.dtotal, guess->g, NCLASS, ws.dgo);
-        G4S_CHECK_LAUNCH("spgemm_validate_bins_kernel");
+        if (!fused_bin) {
+            spgemm_validate_bins_kernel<<<1, 1, 0, stream>>>(dcount, ws.dtotal, guess->g, NCLASS, ws.dgo);
+            G4S_CHECK_LAUNCH("spgemm_validate_bins_kernel");
+        }
         for (int c = 0; c < NCLASS; ++c) ws.hcount[c] = guess->g.count[c];
         ws.hcount[2 * NCLASS] = guess->g.max_work;
         ws.hcount[4 * NCLASS + 1] = guess->g.merge_lists;
@@ -1236,8 +1312,18 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     a.go = guess ? ws.dgo : nullptr;
 
     // ---- symbolic ---------------------------------------------------------------------------------------------
+    if (fused_bin) {
+        b.fused = true;
+        b.fz.class_count = dcount;
+        b.fz.total = ws.dtotal;
+        b.fz.bad = ws.dgo;
+    }
     rc = run_phase(a, b, false, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
     if (rc) return rc;
+    if (fused_bin) {  // the counters exist now: compare them with the guess before anything of the numeric phase runs
+        spgemm_validate_bins_kernel<<<1, 1, 0, stream>>>(dcount, ws.dtotal, guess->g, NCLASS, ws.dgo);
+        G4S_CHECK_LAUNCH("spgemm_validate_bins_kernel");
+    }
     if (phases) G4S_CUDA(cudaEventRecord(ws.ev[2], stream));
 
     // ---- row pointers (scan straight into C) + allocation of C's arrays from the stream-ordered pool --------------
@@ -1412,7 +1498,7 @@ int g4s_compute_flop_device(g4s_csr_t A, g4s_csr_t B, long long *total, int *row
     G4S_CUDA(cudaMallocAsync(&dtotal, sizeof(unsigned long long), stream));
     G4S_CUDA(cudaMemsetAsync(dtotal, 0, sizeof(unsigned long long), stream));
     if (A->rows > 0) {
-        row_work_kernel<<<(A->rows + 255) / 256, 256, 0, stream>>>(A->rowptr, A->colids, B->rowptr, A->rows, B->cols,
+        row_work_kernel<<<std::min((A->rows + 255) / 256, sm_count() * 8), 256, 0, stream>>>(A->rowptr, A->colids, B->rowptr, A->rows, B->cols,
                                                                   row_work_dev, dtotal, nullptr, nullptr, false);
         G4S_CHECK_LAUNCH("row_work_kernel");
     }
