@@ -163,3 +163,36 @@ def test_bad_strips_are_rejected():
         bsr.inspect_host(2, 2, rp, ci, (np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32)))
     with pytest.raises(G4SError):
         bsr.inspect_host(2, 1, rp, ci, None)
+
+
+def test_random_patterns_and_strips_replay_exactly(oracle):
+    """Property test of the inspector: random block patterns (band + noise + duplicates + empty rows), random strip
+    decompositions (random order, ragged lengths), random grids and both CTAs-per-SM settings — the replayed schedule must be
+    A B every time."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 70), st.integers(0, 2 ** 31 - 1), st.integers(1, 7), st.sampled_from([1, 2]), st.booleans())
+    def run(mb, seed, grid, ctas, banded):
+        rng = np.random.default_rng(seed)
+        dens = rng.uniform(0.0, 0.2)
+        pat = sp.random(mb, mb, density=dens, random_state=rng, format="csr")
+        if banded:
+            pat = pat + sp.diags([1.0, 1.0, 1.0], [-1, 0, 1], (mb, mb))
+        pat = pat.tocsr()
+        pat.sort_indices()
+        rp, ci = pat.indptr.astype(np.int32), pat.indices.astype(np.int32)
+        if len(ci) and rng.uniform() < 0.3:  # a duplicated block in some row
+            r = int(rng.integers(0, mb))
+            if rp[r + 1] > rp[r]:
+                ci = np.insert(ci, rp[r], ci[rp[r]])
+                rp = rp.copy()
+                rp[r + 1:] += 1
+        blocks = rng.uniform(-1, 1, (len(ci), 3, 3))
+        perm = rng.permutation(mb).astype(np.int32)
+        ncut = int(rng.integers(0, max(1, mb // 2) + 1))
+        cuts = np.unique(np.concatenate(([0, mb], rng.integers(0, mb + 1, ncut)))).astype(np.int32)
+        check(oracle, mb, rp, ci, blocks, (cuts, perm), grid=grid, ctas=ctas)
+
+    run()
