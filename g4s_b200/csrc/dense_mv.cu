@@ -87,15 +87,19 @@ __global__ void __launch_bounds__(256) upper_tile_kernel(const double *__restric
     double racc = 0.0;
     for (int j0 = max(jc0, (rb * 256) & ~31); j0 < jc1; j0 += 32) {
         double v[32];
+        // all 32 loads of the step first (32 independent 256-byte requests per warp in flight), arithmetic afterwards
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             const int j = j0 + c;
-            double a = 0.0;
-            if (row_ok && j < jc1 && i <= j) a = __ldg(A + col_offset(j, dim, PACKED) + i);
+            v[c] = (row_ok && j < jc1 && i <= j) ? __ldg(A + col_offset(j, dim, PACKED) + i) : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = j0 + c;
             // x[j] is the same for the whole warp: a shared-memory broadcast (a shuffle per column made dsymv 70 % slower than
             // dtrmv, which needs none)
-            if (ROWS && j < jc1) racc = fma(a, j - jc0 < 256 ? xs[j - jc0] : __ldg(x + j), racc);
-            v[c] = (DIAG_IN_COLS || i < j) ? a * xi : 0.0;
+            if (ROWS && j < jc1) racc = fma(v[c], j - jc0 < 256 ? xs[j - jc0] : __ldg(x + j), racc);
+            v[c] = (DIAG_IN_COLS || i < j) ? v[c] * xi : 0.0;
         }
         // halving exchange: after the step with offset o a lane keeps the columns whose bit o equals its own
 #pragma unroll
