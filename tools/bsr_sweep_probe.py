@@ -55,7 +55,9 @@ def main():
         out["kpack_ms"] = ms
         out["kpack_gbs"] = nbytes / ms / 1e6
     t0 = time.perf_counter()
-    strips = bsr.grid_pencil_strips(n, n, 0, n)
+    p0, p1 = int(os.environ.get("PROBE_P0", "4")), int(os.environ.get("PROBE_P1", "4"))
+    strips = bsr.grid_pencil_strips(n, n, 0, n, p0, p1)
+    out["patch"] = [p0, p1]
     plan = bsr.BsrPlan(mb, mb, rp, ci, strips)
     out["plan_create_s"] = time.perf_counter() - t0
     out["set_values_ms"] = timeit(lambda: plan.set_values(blocks.data_ptr()))
