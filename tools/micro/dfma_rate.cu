@@ -1,7 +1,7 @@
 // Micro-benchmark: how fast can ONE warp per scheduler issue independent DFMAs (72 accumulators, 9 x 8 outer product per
+// sub-step, operands in registers), against two warps per scheduler?  Prints cycles per warp-DFMA per scheduler.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/micro/dfma_rate tools/micro/dfma_rate.cu  (measured on B200: 2.639 cycles per
 // warp-DFMA per scheduler with one warp per scheduler, 2.458 with two; 2.0 would be the nominal FP64 rate)
-// sub-step, operands in registers), against two warps per scheduler?  Prints cycles per warp-DFMA per scheduler.
 #include <cstdio>
 #include <cuda_runtime.h>
 template <int ITER>
