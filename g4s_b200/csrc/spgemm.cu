@@ -242,6 +242,7 @@ struct SpgemmArgs {
     int *row_nnz;
     const int *row_work;  // intermediate products per row (sizes the symbolic table)
     int sub_lg;  // lanes cooperating on one row of B (log2), chosen from B's mean row length
+    int b_sorted;   // 1: every row of B has strictly ascending column ids (hence no duplicate column inside a row)
     const int *go;  // null, or a device word: non-zero = the launch parameters were a wrong guess, every kernel returns at once
 };
 #define G4S_SPGEMM_GUARD(a)                         \
@@ -308,6 +309,20 @@ __device__ __forceinline__ void hash_accumulate(int *keys, double *vals, int mas
     atomicAdd(&vals[h], v);
 }
 
+// slot of `key` in the table, claiming an empty slot for it when it is new (the CAS only runs for a key's first occurrence)
+__device__ __forceinline__ int hash_find_or_insert(int *keys, int mask, int key) {
+    int h = hash_slot(key, mask);
+    for (;;) {
+        const int cur = keys[h];
+        if (cur == key) return h;
+        if (cur == -1) {
+            const int old = atomicCAS(&keys[h], -1, key);
+            if (old == -1 || old == key) return h;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
 // GROUP lanes own one row; TABLE slots; WMAX bounds the row's nonzeros (compaction buffer).
 template <int GROUP, int TABLE, int WMAX, int THREADS, bool NUMERIC>
 __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a, const int *__restrict__ list,
@@ -352,7 +367,70 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
         if (lane == 0) cnt[g] = 0;
         group_sync<GROUP>();
         int fresh = 0;
-        if (row >= 0) {
+        if (GROUP == 32 && nsub == 1 && (!NUMERIC || a.b_sorted)) {
+            // Warp per row, the whole warp on ONE row of B at a time.  The row of A is read 32 entries at a time, one per
+            // lane, together with the extents of the rows of B it selects (the dependent chain acol -> brpt is paid once per
+            // 32 entries instead of once per entry), and the first 32 entries of the NEXT row of B are loaded while the
+            // current ones are inserted.
+            // Numeric: B's rows are strictly ascending here (b_sorted; otherwise the atomic path below), so the lanes of an
+            // instruction hit distinct slots and a plain read-modify-write replaces atomicAdd(double) — a compare-and-swap loop
+            // on shared memory (ATOMS.CAST.SPIN.64).  Rows of B are taken one after the other (__syncwarp orders the lanes'
+            // accesses): the sums run over j ascending with one product and one addition per term, the reference's order and
+            // arithmetic (hash_mult.h:579-600), so these rows' VALUES are bit-identical to HashSpGEMM<false,true> as well.
+            const int as = row >= 0 ? __ldg(a.arpt + row) : 0, ae = row >= 0 ? __ldg(a.arpt + row + 1) : 0;
+            for (int j0 = as; j0 < ae; j0 += 32) {
+                int bs_l = 0, be_l = 0;
+                double av_l = 0.0;
+                if (j0 + lane < ae) {
+                    const int k = __ldg(a.acol + j0 + lane);
+                    bs_l = __ldg(a.brpt + k);
+                    be_l = __ldg(a.brpt + k + 1);
+                    if (NUMERIC) av_l = __ldg(a.aval + j0 + lane);
+                }
+                const int cnt_j = min(32, ae - j0);
+                // DEPTH rows of B in flight: their first 32 entries are loaded together (independent loads, one latency for
+                // the batch), then inserted row by row in order
+                constexpr int DEPTH = 4;
+                for (int t0 = 0; t0 < cnt_j; t0 += DEPTH) {
+                    int bsv[DEPTH], bev[DEPTH], colv[DEPTH];
+                    double valv[DEPTH], avv[DEPTH];
+#pragma unroll
+                    for (int d = 0; d < DEPTH; ++d) {
+                        const int t = t0 + d < cnt_j ? t0 + d : cnt_j - 1;
+                        bsv[d] = __shfl_sync(0xffffffffu, bs_l, t);
+                        bev[d] = t0 + d < cnt_j ? __shfl_sync(0xffffffffu, be_l, t) : bsv[d];  // past the end: an empty row
+                        avv[d] = NUMERIC ? __shfl_sync(0xffffffffu, av_l, t) : 0.0;
+                        colv[d] = -1;
+                        valv[d] = 0.0;
+                        if (bsv[d] + lane < bev[d]) {
+                            colv[d] = __ldg(a.bcol + bsv[d] + lane);
+                            if (NUMERIC) valv[d] = __ldg(a.bval + bsv[d] + lane);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < DEPTH; ++d) {
+                        int col = colv[d];
+                        double val = valv[d];
+                        for (int p = bsv[d] + lane;; p += 32) {  // first trip: the prefetched entry; further trips: rows beyond 32
+                            if (p >= bsv[d] + 32) {
+                                if (p >= bev[d]) break;
+                                col = __ldg(a.bcol + p);
+                                if (NUMERIC) val = __ldg(a.bval + p);
+                            } else if (p >= bev[d]) {
+                                break;
+                            }
+                            if (NUMERIC) {
+                                const int h = hash_find_or_insert(mykeys, mask, col);
+                                myvals[h] = __dadd_rn(__dmul_rn(avv[d], val), myvals[h]);
+                            } else {
+                                fresh += hash_insert(mykeys, mask, col);
+                            }
+                        }
+                        if (NUMERIC) __syncwarp();
+                    }
+                }
+            }
+        } else if (row >= 0) {
             const int as = __ldg(a.arpt + row), ae = __ldg(a.arpt + row + 1);
             for (int j = as + my_sub; j < ae; j += nsub) {
                 const int k = __ldg(a.acol + j);
@@ -393,13 +471,35 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
             group_sync<GROUP>();
             const int n = nrow;
             if (n <= 128) {
-                // short rows: rank sort straight into C's row (n^2 / GROUP comparisons, no barriers)
-                for (int e = lane; e < n; e += GROUP) {
-                    const int key = myck[e];
-                    int rank = 0;
-                    for (int f = 0; f < n; ++f) rank += myck[f] < key;
-                    a.ccol[out + rank] = key;
-                    a.cval[out + rank] = mycv[e];
+                // short rows: rank sort straight into C's row (no barriers).  A warp keeps its up to four elements in registers
+                // and broadcasts every key once (ncu: the one-element-at-a-time form of this loop was ~40 % of the numeric
+                // kernel's 5 300 instructions per 125-entry row)
+                if (GROUP == 32) {
+                    int key4[4], rank4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        key4[q] = lane + 32 * q < n ? myck[lane + 32 * q] : 0x7fffffff;
+                        rank4[q] = 0;
+                    }
+                    for (int f = 0; f < n; ++f) {
+                        const int kf = myck[f];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rank4[q] += kf < key4[q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < n) {
+                            a.ccol[out + rank4[q]] = key4[q];
+                            a.cval[out + rank4[q]] = mycv[lane + 32 * q];
+                        }
+                } else {
+                    for (int e = lane; e < n; e += GROUP) {
+                        const int key = myck[e];
+                        int rank = 0;
+                        for (int f = 0; f < n; ++f) rank += myck[f] < key;
+                        a.ccol[out + rank] = key;
+                        a.cval[out + rank] = mycv[e];
+                    }
                 }
             } else {
                 // longer rows: bitonic sort of the compacted (column, value) pairs in shared memory
@@ -1309,6 +1409,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     a.row_nnz = row_nnz;
     a.row_work = b.row_work;
     a.sub_lg = sub_lg;
+    a.b_sorted = B->sorted_cols == 1 ? 1 : 0;
     a.go = guess ? ws.dgo : nullptr;
 
     // ---- symbolic ---------------------------------------------------------------------------------------------

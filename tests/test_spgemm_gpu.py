@@ -250,3 +250,18 @@ def test_repeated_product_reuses_host_decisions_and_survives_a_changed_pattern(g
     assert not np.array_equal(rpt, rpt2)
     for _ in range(2):
         check_against(g4s.HashSpGEMM(Ad, Bd).to_host(), rpt2, col2, val2, scale2)
+
+
+def test_warp_per_row_class_is_bit_exact_when_b_is_sorted(g4s, oracle):
+    """Class 3 (warp per row, shared-memory table): when B's rows are strictly ascending the warp walks one row of B per
+    step, so the slots of an instruction are distinct, the sums run over j ascending with one product and one addition
+    per term, and the values equal HashSpGEMM<false,true>'s bit for bit — no atomicAdd(double) left on that path.
+    27-point A*A rows: 729 products, 125 columns."""
+    A = laplacian_3d_27(9)
+    rng = np.random.default_rng(21)
+    A = (A[0], A[1], A[2], A[3], rng.uniform(-1, 1, len(A[3])))      # non-trivial values: rounding order matters
+    rpt, col, val = oracle.hash_spgemm(A, A)
+    C = g4s.HashSpGEMM(as_csr(g4s, A), as_csr(g4s, A)).to_host()
+    np.testing.assert_array_equal(C.rowptr, rpt)
+    np.testing.assert_array_equal(C.colids, col)
+    np.testing.assert_array_equal(C.values, val)
