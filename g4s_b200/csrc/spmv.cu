@@ -138,11 +138,35 @@ __global__ void scan_apply_kernel(const int *__restrict__ in, int *__restrict__ 
 }
 
 // exclusive scan of n int32 counts; total (64-bit) returned through *total_host when non-null (synchronises).
+// Scratch for the tile sums, kept per (thread, device, stream): a scan is part of every SpGEMM product and of every radix-sort
+// pass, and a cudaMallocAsync / cudaFreeAsync pair per call was two of the ~16 runtime calls of a repeated product.
+struct ScanScratch {
+    long long *buf = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+};
+static thread_local ScanScratch t_scan;
+
 int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, long long *total_host,
                        cudaStream_t stream) {
     const int ntiles = (int)std::max<long long>(1, (n + SCAN_TILE - 1) / SCAN_TILE);
-    long long *tile_sums = nullptr;
-    G4S_CUDA(cudaMallocAsync(&tile_sums, sizeof(long long) * ((size_t)ntiles + 1), stream));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ScanScratch &sc = t_scan;
+    if (sc.device != dev || sc.stream != stream || sc.cap < (size_t)ntiles + 1) {
+        // another device / stream / size: the old buffer may still be in use by work queued on its stream, so it is released
+        // in that stream's order and a new one is taken in this stream's order
+        if (sc.buf && sc.device == dev) cudaFreeAsync(sc.buf, sc.stream);
+        sc.buf = nullptr;
+        sc.cap = 0;
+        const size_t want = std::max<size_t>((size_t)ntiles + 1, 4096);
+        G4S_CUDA(cudaMallocAsync(&sc.buf, sizeof(long long) * want, stream));
+        sc.cap = want;
+        sc.device = dev;
+        sc.stream = stream;
+    }
+    long long *tile_sums = sc.buf;
     scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, stream>>>(in, n, tile_sums);
     G4S_CHECK_LAUNCH("scan_tile_sums_kernel");
     scan_tile_offsets_kernel<<<1, 1024, 0, stream>>>(tile_sums, ntiles);
@@ -153,7 +177,6 @@ int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, lo
         G4S_CUDA(cudaMemcpyAsync(total_host, tile_sums + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, stream));
         G4S_CUDA(cudaStreamSynchronize(stream));
     }
-    G4S_CUDA(cudaFreeAsync(tile_sums, stream));
     return G4S_OK;
 }
 
