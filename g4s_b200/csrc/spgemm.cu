@@ -687,15 +687,18 @@ struct MergeFused {
     unsigned long long *total;
     int *bad;
 };
-template <int K, bool NUMERIC, bool FUSED = false>
+template <int K, bool NUMERIC, bool FUSED = false, bool PF = false>
 __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
                                                                int nlist, const MergeFused fz = MergeFused()) {
     G4S_SPGEMM_GUARD(a);
     constexpr int THREADS = 256;
     unsigned long long f_sum = 0;
     int f_max = 0, f_len = 0, f_rows = 0;
-    // numeric phase: [MERGE_STAGE][THREADS] columns and values; entry e of lane L sits in column (L + e) & 31 of its
-    // warp's 32 columns, so that both the per-thread writes and the warp's read-back are bank-conflict-free
+    // numeric phase: every warp stages the output of its 32 consecutive rows in shared memory — MERGE_STAGE * 32 entries,
+    // COMPACT, in the order they have in C (a row's first position is known from C's row pointers before its merge
+    // starts) — and then copies the stretch to C with plain coalesced stores.  (The first version staged entry e of lane L
+    // transposed at [e][(L + e) & 31] and found each output's owner lane with a 5-step shuffle search: 56 instructions per
+    // 32 outputs, 38 % of the kernel's instructions, and 3-4 shared-memory wavefronts per read-back; ncu of round 2.)
     // (13 staged entries per row for the 5-list instance — 40 KB per CTA, a fifth CTA per SM at 46 registers — was measured:
     // numeric 0.43 -> 0.55 ms on configs[3]; the register cap costs more than the extra warps give)
     constexpr int MERGE_STAGE = MERGE_STAGE_MAX;
@@ -711,12 +714,13 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
             as = __ldg(a.arpt + row);
             na = __ldg(a.arpt + row + 1) - as;
         }
-        int pos[K], end[K], head[K];
+        int pos[K], end[K], head[K], nxt[PF ? K : 1];
         double av[K];
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             pos[u] = end[u] = 0;
             head[u] = 0x7fffffff;
+            if (PF) nxt[u] = 0x7fffffff;
             av[u] = 0.0;
             if (u < na) {
                 const int k = __ldg(a.acol + as + u);
@@ -724,6 +728,7 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
                 pos[u] = __ldg(a.brpt + k);
                 end[u] = __ldg(a.brpt + k + 1);
                 if (pos[u] < end[u]) head[u] = __ldg(a.bcol + pos[u]);
+                if (PF && pos[u] + 1 < end[u]) nxt[u] = __ldg(a.bcol + pos[u] + 1);
             }
         }
         if (FUSED && active) {
@@ -737,16 +742,18 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
             f_len = max(f_len, na);
             ++f_rows;
         }
-        int out = 0, nrow = 0;
+        int out = 0, nrow = 0, span = 0, stage_at = 0;
         bool staged = false;
         if (NUMERIC) {
             if (active) {
                 out = __ldg(a.crpt + row);
                 nrow = __ldg(a.crpt + row + 1) - out;
             }
-            // the warp's 32 rows are consecutive (one contiguous range of C) and short: stage, then store coalesced
-            const int row0 = __shfl_sync(0xffffffffu, row, 0);
-            staged = __all_sync(0xffffffffu, active && row == row0 + lane && nrow <= MERGE_STAGE);
+            // the warp's 32 rows are consecutive (one contiguous stretch of C) and the stretch fits: stage, then copy
+            const int row0 = __shfl_sync(0xffffffffu, row, 0), out0 = __shfl_sync(0xffffffffu, out, 0);
+            span = __shfl_sync(0xffffffffu, out + nrow, 31) - out0;
+            staged = __all_sync(0xffffffffu, active && row == row0 + lane) && span <= MERGE_STAGE * 32;
+            stage_at = tw * MERGE_STAGE + (out - out0);
         }
         int n = 0;
         for (;;) {
@@ -765,14 +772,18 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
                         first = false;
                     }
                     ++pos[u];
-                    head[u] = pos[u] < end[u] ? __ldg(a.bcol + pos[u]) : 0x7fffffff;
+                    if (PF) {  // the list's next head was loaded when its current one became head: off the critical path
+                        head[u] = nxt[u];
+                        nxt[u] = pos[u] + 1 < end[u] ? __ldg(a.bcol + pos[u] + 1) : 0x7fffffff;
+                    } else {
+                        head[u] = pos[u] < end[u] ? __ldg(a.bcol + pos[u]) : 0x7fffffff;
+                    }
                 }
             }
             if (NUMERIC) {
                 if (staged) {
-                    const int col = tw + ((lane + n) & 31);
-                    s_col[n * THREADS + col] = m;
-                    s_val[n * THREADS + col] = v;
+                    s_col[stage_at + n] = m;
+                    s_val[stage_at + n] = v;
                 } else {
                     a.ccol[out + n] = m;
                     a.cval[out + n] = v;
@@ -787,23 +798,9 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
         if (staged) {
             __syncwarp();
             const int out0 = __shfl_sync(0xffffffffu, out, 0);
-            const int out1 = __shfl_sync(0xffffffffu, out + nrow, 31);
-            for (int ob = out0; ob < out1; ob += 32) {  // warp-uniform trip count: the owner search uses shuffles
-                const int o = min(ob + lane, out1 - 1);
-                int lo = 0, hi = 31;  // owner lane = last lane whose row starts at or before o
-#pragma unroll
-                for (int step = 0; step < 5; ++step) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    const int start_mid = __shfl_sync(0xffffffffu, out, mid);
-                    if (start_mid <= o) lo = mid;
-                    else hi = mid - 1;
-                }
-                const int e = o - __shfl_sync(0xffffffffu, out, lo);
-                if (ob + lane < out1) {
-                    const int col = tw + ((lo + e) & 31);
-                    a.ccol[o] = s_col[e * THREADS + col];
-                    a.cval[o] = s_val[e * THREADS + col];
-                }
+            for (int i = lane; i < span; i += 32) {
+                a.ccol[out0 + i] = s_col[tw * MERGE_STAGE + i];
+                a.cval[out0 + i] = s_val[tw * MERGE_STAGE + i];
             }
             __syncwarp();
         }
@@ -1119,7 +1116,9 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
     if (b.count[1]) {
         const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
         const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
-        if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        static const bool pf = [] { const char *e = getenv("G4S_SPGEMM_MERGE_PF"); return e && atoi(e) != 0; }();
+        if (numeric && k5 && pf) spgemm_merge_row_kernel<5, true, false, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (b.fused && k5)
             spgemm_merge_row_kernel<5, false, true><<<std::min(grid, sm_count() * 8), 256, 0, stream>>>(a, list(1), b.count[1], b.fz);

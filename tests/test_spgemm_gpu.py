@@ -265,3 +265,75 @@ def test_warp_per_row_class_is_bit_exact_when_b_is_sorted(g4s, oracle):
     np.testing.assert_array_equal(C.rowptr, rpt)
     np.testing.assert_array_equal(C.colids, col)
     np.testing.assert_array_equal(C.values, val)
+
+
+def short_rows(rows, cols, max_len, seed):
+    """Every row holds 1..max_len strictly ascending columns: with max_len <= 8 (and products <= 64) all rows of A*B are
+    in the merge class, and their outputs range from 1 to 64 entries — past the 16 the kernels stage per row."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, max_len + 1, rows)
+    rowptr = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    col = np.concatenate([np.sort(rng.choice(cols, size=k, replace=False)) for k in lens])
+    return (rows, cols, rowptr.astype(np.int32), col.astype(np.int32), rng.uniform(-1, 1, len(col)))
+
+
+MERGE_CLASS_CASES = {
+    "lap2d_64": lambda: (laplacian_2d(64),) * 2,                                     # 4096 rows: full warps
+    "lap2d_45": lambda: (laplacian_2d(45),) * 2,                                     # 2025 rows: ragged last CTA and warp
+    "tridiag3": lambda: (tridiag3(),) * 2,                                           # one partial warp
+    "short_rows_long_outputs": lambda: (short_rows(3001, 700, 8, 11), short_rows(700, 5000, 8, 12)),  # up to 64 outputs a row
+    "short_rows_dense_cols": lambda: (short_rows(1500, 300, 6, 13), short_rows(300, 40, 7, 14)),      # many coinciding columns
+}
+
+
+@pytest.mark.parametrize("name", sorted(MERGE_CLASS_CASES))
+def test_merge_class_product_is_bit_exact_first_and_repeated(g4s, oracle, name):
+    """Every row in the merge class (one thread per row, k-way merge of sorted rows of B, output staged compactly per warp
+    and stored coalesced; spgemm.cu: spgemm_merge_row_kernel).  Row pointers, columns AND values must be those of
+    HashSpGEMM<false,true> bit for bit (the merge keeps the reference's accumulation order), on the first product (host
+    decisions read back) and on the repeated ones (decisions guessed, binning fused into the symbolic kernel).  The cases
+    cover warps whose 32 rows' output exceeds the staging stretch (direct stores) and ragged tails."""
+    A, B = MERGE_CLASS_CASES[name]()
+    rpt, col, val = oracle.hash_spgemm(A, B)
+    Ad, Bd = as_csr(g4s, A), as_csr(g4s, B)
+    for _ in range(4):
+        C = g4s.HashSpGEMM(Ad, Bd).to_host()
+        np.testing.assert_array_equal(C.rowptr, rpt)
+        np.testing.assert_array_equal(C.colids, col)
+        np.testing.assert_array_equal(C.values, val)
+
+
+def test_repeated_merge_class_product_survives_changed_operands(g4s, oracle):
+    """The repeated all-merge-class product allocates C from the previous product's nnz(C) and lets the symbolic kernel do the
+    binning.  When B's pattern is rewritten in place under the same handle (same nnz, other columns) the device must
+    notice (nnz differs) before the numeric phase writes anything, and the product must come out exact."""
+    import torch
+
+    from g4s_b200.dist import _DevArray
+
+    A = short_rows(2100, 600, 5, 21)
+    B = short_rows(600, 900, 6, 22)
+    Ad, Bd = as_csr(g4s, A), as_csr(g4s, B)
+    rpt, col, val = oracle.hash_spgemm(A, B)
+    for _ in range(3):
+        C = g4s.HashSpGEMM(Ad, Bd).to_host()
+        assert np.array_equal(C.rowptr, rpt) and np.array_equal(C.colids, col) and np.array_equal(C.values, val)
+    # squeeze B's columns into a fifth of the width, keeping every row strictly ascending: far more coinciding columns
+    rng = np.random.default_rng(23)
+    new_cols = np.concatenate([np.sort(rng.choice(180, size=k, replace=False)) for k in np.diff(B[2])]).astype(np.int32)
+    _, ci, _ = Bd.device_arrays()
+    torch.as_tensor(_DevArray(ci, len(new_cols), "<i4"), device="cuda").copy_(torch.from_numpy(new_cols).cuda())
+    torch.cuda.synchronize()
+    B2 = (B[0], B[1], B[2], new_cols, B[4])
+    rpt2, col2, val2 = oracle.hash_spgemm(A, B2)
+    assert rpt2[-1] < rpt[-1]
+    for _ in range(3):
+        C = g4s.HashSpGEMM(Ad, Bd).to_host()
+        assert np.array_equal(C.rowptr, rpt2) and np.array_equal(C.colids, col2) and np.array_equal(C.values, val2)
+    # and the other way round (more entries than the previous product had: the capacity guard)
+    torch.as_tensor(_DevArray(ci, len(new_cols), "<i4"), device="cuda").copy_(torch.from_numpy(B[3]).cuda())
+    torch.cuda.synchronize()
+    for _ in range(2):
+        C = g4s.HashSpGEMM(Ad, Bd).to_host()
+        assert np.array_equal(C.rowptr, rpt) and np.array_equal(C.colids, col) and np.array_equal(C.values, val)
