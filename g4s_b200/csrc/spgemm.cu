@@ -700,7 +700,10 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
     // transposed at [e][(L + e) & 31] and found each output's owner lane with a 5-step shuffle search: 56 instructions per
     // 32 outputs, 38 % of the kernel's instructions, and 3-4 shared-memory wavefronts per read-back; ncu of round 2.)
     // (13 staged entries per row for the 5-list instance — 40 KB per CTA, a fifth CTA per SM at 46 registers — was measured:
-    // numeric 0.43 -> 0.55 ms on configs[3]; the register cap costs more than the extra warps give)
+    // numeric 0.43 -> 0.55 ms on configs[3]; the register cap costs more than the extra warps give.  Staging the rows of B as
+    // well — coalesced copies of the contiguous stretches the warp's lists form, overlapping stretches stored once, 6.9 KB
+    // per warp, merge out of shared memory — was rebuilt in round 2 and measured again: parity-green, 0.53 against 0.38 ms;
+    // 16 warps per SM with one tile each keep too few bytes in flight.)
     constexpr int MERGE_STAGE = MERGE_STAGE_MAX;
     __shared__ int s_col[NUMERIC ? MERGE_STAGE * THREADS : 1];
     __shared__ double s_val[NUMERIC ? MERGE_STAGE * THREADS : 1];
@@ -1116,7 +1119,9 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
     if (b.count[1]) {
         const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
         const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
-        static const bool pf = [] { const char *e = getenv("G4S_SPGEMM_MERGE_PF"); return e && atoi(e) != 0; }();
+        // G4S_SPGEMM_MERGE_PF=0: the numeric 5-list instance without the next-head prefetch (0.379 against 0.369 ms)
+        const char *pe = getenv("G4S_SPGEMM_MERGE_PF");  // read per call: the tests run both instances
+        const bool pf = !pe || atoi(pe) != 0;
         if (numeric && k5 && pf) spgemm_merge_row_kernel<5, true, false, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);

@@ -284,16 +284,22 @@ MERGE_CLASS_CASES = {
     "tridiag3": lambda: (tridiag3(),) * 2,                                           # one partial warp
     "short_rows_long_outputs": lambda: (short_rows(3001, 700, 8, 11), short_rows(700, 5000, 8, 12)),  # up to 64 outputs a row
     "short_rows_dense_cols": lambda: (short_rows(1500, 300, 6, 13), short_rows(300, 40, 7, 14)),      # many coinciding columns
+    "tridiag_times_short": lambda: (to_tuple(sp.diags([1.5, -2.0, 0.5], [-1, 0, 1], shape=(900, 900))),
+                                    short_rows(900, 1200, 8, 15)),   # contiguous stretches of B of uneven rows, overlapping
+    "lap2d_times_shifted": lambda: (laplacian_2d(40), to_tuple(sp.diags([1.0, 2.0, 3.0, 4.0], [-37, -1, 2, 50], shape=(1600, 1600)))),
 }
 
 
+@pytest.mark.parametrize("prefetch", ["1", "0"])
 @pytest.mark.parametrize("name", sorted(MERGE_CLASS_CASES))
-def test_merge_class_product_is_bit_exact_first_and_repeated(g4s, oracle, name):
+def test_merge_class_product_is_bit_exact_first_and_repeated(g4s, oracle, monkeypatch, name, prefetch):
     """Every row in the merge class (one thread per row, k-way merge of sorted rows of B, output staged compactly per warp
     and stored coalesced; spgemm.cu: spgemm_merge_row_kernel).  Row pointers, columns AND values must be those of
     HashSpGEMM<false,true> bit for bit (the merge keeps the reference's accumulation order), on the first product (host
     decisions read back) and on the repeated ones (decisions guessed, binning fused into the symbolic kernel).  The cases
-    cover warps whose 32 rows' output exceeds the staging stretch (direct stores) and ragged tails."""
+    cover warps whose 32 rows' output exceeds the staging stretch (direct stores) and ragged tails.  Both numeric 5-list instances
+    (with and without the next-head prefetch, G4S_SPGEMM_MERGE_PF)."""
+    monkeypatch.setenv("G4S_SPGEMM_MERGE_PF", prefetch)
     A, B = MERGE_CLASS_CASES[name]()
     rpt, col, val = oracle.hash_spgemm(A, B)
     Ad, Bd = as_csr(g4s, A), as_csr(g4s, B)
