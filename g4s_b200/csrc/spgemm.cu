@@ -687,7 +687,7 @@ struct MergeFused {
     unsigned long long *total;
     int *bad;
 };
-template <int K, bool NUMERIC, bool FUSED = false, bool PF = false>
+template <int K, bool NUMERIC, bool FUSED = false, int PF = 0>
 __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_row_kernel(const SpgemmArgs a, const int *__restrict__ list,
                                                                int nlist, const MergeFused fz = MergeFused()) {
     G4S_SPGEMM_GUARD(a);
@@ -718,7 +718,13 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
             na = __ldg(a.arpt + row + 1) - as;
         }
         int pos[K], end[K], head[K], nxt[PF ? K : 1];
-        double av[K];
+        // PF >= 1: a list's next column id is loaded when its current one becomes the head (the reload leaves the min -> compare
+        // -> reload chain); PF == 2: the VALUE under every head is loaded at that moment too, one or more merge steps before
+        // the head is taken — a warp issues in order, so a value gathered at the moment of use held up the whole step behind
+        // the staging store (numeric 0.379 -> 0.369 with PF 1 -> 0.334 ms with PF 2 on configs[3]; 72 registers, 3 CTAs per SM.
+        // Measured and dropped: the value behind the next column as well, 0.345; the next block's row extents fetched during
+        // the merge, 0.341; PF 2 squeezed into 63 registers for 4 CTAs per SM, 0.341)
+        double av[K], hval[PF >= 2 ? K : 1];
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             pos[u] = end[u] = 0;
@@ -731,6 +737,7 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
                 pos[u] = __ldg(a.brpt + k);
                 end[u] = __ldg(a.brpt + k + 1);
                 if (pos[u] < end[u]) head[u] = __ldg(a.bcol + pos[u]);
+                if (PF >= 2 && pos[u] < end[u]) hval[u] = __ldg(a.bval + pos[u]);
                 if (PF && pos[u] + 1 < end[u]) nxt[u] = __ldg(a.bcol + pos[u] + 1);
             }
         }
@@ -770,13 +777,14 @@ __global__ void __launch_bounds__(256, (NUMERIC || K > 5) ? 1 : 8) spgemm_merge_
             for (int u = 0; u < K; ++u) {
                 if (head[u] == m) {
                     if (NUMERIC) {
-                        const double prod = __dmul_rn(av[u], __ldg(a.bval + pos[u]));
+                        const double prod = __dmul_rn(av[u], PF >= 2 ? hval[u] : __ldg(a.bval + pos[u]));
                         v = first ? prod : __dadd_rn(prod, v);
                         first = false;
                     }
                     ++pos[u];
                     if (PF) {  // the list's next head was loaded when its current one became head: off the critical path
                         head[u] = nxt[u];
+                        if (PF >= 2 && pos[u] < end[u]) hval[u] = __ldg(a.bval + pos[u]);
                         nxt[u] = pos[u] + 1 < end[u] ? __ldg(a.bcol + pos[u] + 1) : 0x7fffffff;
                     } else {
                         head[u] = pos[u] < end[u] ? __ldg(a.bcol + pos[u]) : 0x7fffffff;
@@ -1119,10 +1127,11 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
     if (b.count[1]) {
         const int grid = (int)std::min<long long>(((long long)b.count[1] + 255) / 256, (long long)sm_count() * 32);
         const bool k5 = b.merge_lists <= 5 && !getenv("G4S_SPGEMM_K8");
-        // G4S_SPGEMM_MERGE_PF=0: the numeric 5-list instance without the next-head prefetch (0.379 against 0.369 ms)
+        // G4S_SPGEMM_MERGE_PF = 0 / 1 / 2 (default): prefetch depth of the numeric 5-list instance, see the kernel
         const char *pe = getenv("G4S_SPGEMM_MERGE_PF");  // read per call: the tests run both instances
-        const bool pf = !pe || atoi(pe) != 0;
-        if (numeric && k5 && pf) spgemm_merge_row_kernel<5, true, false, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        const int pf = pe ? atoi(pe) : 2;
+        if (numeric && k5 && pf >= 2) spgemm_merge_row_kernel<5, true, false, 2><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
+        else if (numeric && k5 && pf) spgemm_merge_row_kernel<5, true, false, 1><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric && k5) spgemm_merge_row_kernel<5, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (numeric) spgemm_merge_row_kernel<MERGE_MAX_A, true><<<grid, 256, 0, stream>>>(a, list(1), b.count[1]);
         else if (b.fused && k5)

@@ -290,7 +290,7 @@ MERGE_CLASS_CASES = {
 }
 
 
-@pytest.mark.parametrize("prefetch", ["1", "0"])
+@pytest.mark.parametrize("prefetch", ["2", "1", "0"])
 @pytest.mark.parametrize("name", sorted(MERGE_CLASS_CASES))
 def test_merge_class_product_is_bit_exact_first_and_repeated(g4s, oracle, monkeypatch, name, prefetch):
     """Every row in the merge class (one thread per row, k-way merge of sorted rows of B, output staged compactly per warp
