@@ -18,6 +18,7 @@
 //  * Pieces of a long row leave partial sums in carry[chunk]; one thread per long row adds them in order
 //    (deterministic; no atomics anywhere).
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -769,6 +770,10 @@ __global__ void spmv_warp_row_kernel(const int *__restrict__ rowptr, const int *
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+// CTAs a launch may use, in percent of the full persistent grid (0: all).  The pipelined host-pointer product throttles its
+// row-block launches: a block's product only has to finish before the next block of x has arrived, and a kernel that
+// saturates HBM slows the host link's DMA down while it runs (spmv_host_pipelined).
+static thread_local int t_grid_percent = 0;
 template <int CAP, int NBUF, int WARPS>
 static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm, cudaStream_t stream,
                                const XParts *parts = nullptr) {
@@ -790,6 +795,7 @@ static int launch_chunk_kernel(const SpmvArgs &args, bool accum, int ctas_per_sm
     }
     long long want = ((long long)(args.nchunks - args.chunk_begin) + WARPS - 1) / WARPS;
     int grid = (int)std::min<long long>(want, (long long)sm_count() * ctas_per_sm);
+    if (t_grid_percent > 0) grid = (int)(((long long)grid * t_grid_percent + 99) / 100);
     if (grid < 1) grid = 1;
     XParts none;
     none.world = 0;
@@ -1152,6 +1158,16 @@ __global__ void block_colmax_kernel(const int2 *__restrict__ desc, const int *__
 }
 
 struct HostPipe {
+    // share of the persistent grid a row-block launch gets (percent).  A block's product only has to be done before the next
+    // block of x has arrived; launched at full width it saturates HBM in bursts and the host link's DMA — which pays for the
+    // whole call — runs at about half speed while it does (trace: 16 MB of x in 0.395 ms instead of 0.34).  The first calls
+    // try 100 / 50 / 25 % twice each and the fastest setting stays (n = 400 27-point Laplacian: 12.2 ms at 100 and 50 %,
+    // 11.1-11.7 ms at 25 % = one CTA on every other SM; the floor of the two copies alone, chained block by block, is 10.8 ms)
+    static constexpr int N_TRY = 3;
+    int try_pct[N_TRY] = {100, 50, 25};
+    double try_best[N_TRY] = {1e30, 1e30, 1e30};
+    int calls = 0, pct = 100;
+    bool progressive = false;  // blocks become ready while x is still arriving (banded matrices): throttling can pay
     int nb = 0, chunks_per_block = 0;
     std::vector<int> colmax, row_end;  // per block: highest column referenced (running max), one past its last row
     cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
@@ -1166,7 +1182,11 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
     HostPipe *&hp = h->host_pipe;
     if (!hp) {
         hp = new HostPipe();
-        hp->nb = std::max(1, std::min(32, p.nchunks / 4096));
+        static const int max_blocks = [] {  // G4S_SPMV_HOST_BLOCKS: row blocks of the pipelined host-pointer product
+            const char *e = getenv("G4S_SPMV_HOST_BLOCKS");
+            return e && atoi(e) > 0 ? atoi(e) : 32;
+        }();
+        hp->nb = std::max(1, std::min(max_blocks, p.nchunks / 4096));
         hp->chunks_per_block = (p.nchunks + hp->nb - 1) / hp->nb;
         hp->nb = (p.nchunks + hp->chunks_per_block - 1) / hp->chunks_per_block;
         int *dmax = nullptr;
@@ -1189,6 +1209,7 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
             if (b) hp->colmax[b] = std::max(hp->colmax[b], hp->colmax[b - 1]);
         }
         hp->row_end[hp->nb - 1] = h->rows;
+        hp->progressive = hp->nb >= 4 && (long long)hp->colmax[hp->nb / 2] + 1 < (long long)h->cols * 9 / 10;
         G4S_CUDA(cudaStreamCreateWithFlags(&hp->up, cudaStreamNonBlocking));
         G4S_CUDA(cudaStreamCreateWithFlags(&hp->comp, cudaStreamNonBlocking));
         G4S_CUDA(cudaStreamCreateWithFlags(&hp->down, cudaStreamNonBlocking));
@@ -1210,6 +1231,24 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
     const bool defer_download = p.n_long > 0;  // the long-row fix-up touches y after every block has run
     long long uploaded = 0;
     int row0 = 0;
+    // G4S_SPMV_HOST_TRACE=1: per-block completion times of the three streams on stderr (diagnostic; timing events per call)
+    static const bool trace = [] { const char *e = getenv("G4S_SPMV_HOST_TRACE"); return e && atoi(e) != 0; }();
+    std::vector<cudaEvent_t> tr;
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tr.push_back(e);
+    };
+    mark(hp->up);
+    static const int fixed_pct = [] {  // G4S_SPMV_HOST_GRID_PERCENT: fixes the share instead of trying
+        const char *e = getenv("G4S_SPMV_HOST_GRID_PERCENT");
+        return e && atoi(e) > 0 ? std::min(100, atoi(e)) : 0;
+    }();
+    const bool trying = hp->progressive && !fixed_pct && hp->calls < 2 * HostPipe::N_TRY;
+    const int call_pct = fixed_pct ? fixed_pct : (trying ? hp->try_pct[hp->calls % HostPipe::N_TRY] : hp->pct);
+    const auto t_call = std::chrono::steady_clock::now();
     for (int b = 0; b < hp->nb; ++b) {
         const long long need = std::min<long long>((long long)hp->colmax[b] + 1, h->cols);
         if (need > uploaded) {
@@ -1218,17 +1257,22 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
             uploaded = need;
         }
         G4S_CUDA(cudaEventRecord(hp->ev_up[b], hp->up));
+        mark(hp->up);
         G4S_CUDA(cudaStreamWaitEvent(hp->comp, hp->ev_up[b], 0));
         const int c0 = b * hp->chunks_per_block, c1 = std::min(c0 + hp->chunks_per_block, p.nchunks);
+        t_grid_percent = (hp->progressive && b + 1 < hp->nb) ? call_pct : 0;  // the last block is on the critical path: full speed
         rc = spmv_run(h, h->x_dev, h->y_dev, nullptr, false, hp->comp, nullptr, c0, c1);
+        t_grid_percent = 0;
         if (rc) return rc;
         G4S_CUDA(cudaEventRecord(hp->ev_comp[b], hp->comp));
+        mark(hp->comp);
         if (!defer_download && hp->row_end[b] > row0) {
             G4S_CUDA(cudaStreamWaitEvent(hp->down, hp->ev_comp[b], 0));
             G4S_CUDA(cudaMemcpyAsync(y + row0, h->y_dev + row0, sizeof(double) * (size_t)(hp->row_end[b] - row0),
                                      cudaMemcpyDeviceToHost, hp->down));
             row0 = hp->row_end[b];
         }
+        mark(hp->down);
     }
     if (defer_download) {
         spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, hp->comp>>>(p.long_rows, p.n_long, p.carry, nullptr, h->y_dev);
@@ -1238,6 +1282,26 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
     }
     G4S_CUDA(cudaStreamSynchronize(hp->down));
     G4S_CUDA(cudaStreamSynchronize(hp->comp));
+    if (trying) {
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
+        double &best = hp->try_best[hp->calls % HostPipe::N_TRY];
+        best = std::min(best, secs);
+        if (++hp->calls == 2 * HostPipe::N_TRY) {
+            int k = 0;
+            for (int q = 1; q < HostPipe::N_TRY; ++q)
+                if (hp->try_best[q] < hp->try_best[k] * 0.98) k = q;  // a narrower grid has to win by 2 %
+            hp->pct = hp->try_pct[k];
+        }
+    }
+    if (trace) {
+        fprintf(stderr, "g4s_spmv_host trace (ms since the first copy was queued): block  upload  product  download\n");
+        for (int b = 0; b < hp->nb; ++b) {
+            float t[3] = {0, 0, 0};
+            for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], tr[0], tr[1 + 3 * b + k]);
+            fprintf(stderr, "  %3d  %8.3f  %8.3f  %8.3f\n", b, t[0], t[1], t[2]);
+        }
+        for (auto e : tr) cudaEventDestroy(e);
+    }
     return G4S_OK;
 }
 
