@@ -1158,19 +1158,18 @@ __global__ void block_colmax_kernel(const int2 *__restrict__ desc, const int *__
 }
 
 struct HostPipe {
-    // share of the persistent grid a row-block launch gets (percent).  A block's product only has to be done before the next
-    // block of x has arrived; launched at full width it saturates HBM in bursts and the host link's DMA — which pays for the
-    // whole call — runs at about half speed while it does (trace: 16 MB of x in 0.395 ms instead of 0.34).  The first calls
-    // try 100 / 50 / 25 % twice each and the fastest setting stays (n = 400 27-point Laplacian: 12.2 ms at 100 and 50 %,
-    // 11.1-11.7 ms at 25 % = one CTA on every other SM; the floor of the two copies alone, chained block by block, is 10.8 ms)
-    static constexpr int N_TRY = 3;
-    int try_pct[N_TRY] = {100, 50, 25};
-    double try_best[N_TRY] = {1e30, 1e30, 1e30};
-    int calls = 0, pct = 100;
-    bool progressive = false;  // blocks become ready while x is still arriving (banded matrices): throttling can pay
+    // Row-block launches of a banded matrix get a QUARTER of the persistent grid each and go round-robin over four compute
+    // streams.  A block's product only has to be done before the next block of x has arrived; launched at full width it
+    // saturates HBM in bursts and the host link's DMA — which pays for the whole call — runs at about half speed while it does
+    // (trace: 16 MB of x in 0.395 ms instead of 0.34; n = 400 27-point Laplacian 12.2-12.8 ms at full width, 11.1-11.8 ms at
+    // a quarter = one CTA on every other SM; the two copies alone, chained block by block, take 10.8 ms).  If a narrow
+    // product is not done when the next block of x is, the next product starts beside it on another stream: the width grows
+    // by itself up to the whole grid, so a matrix (or a clock state) with slower products never waits for a throttled kernel.
+    static constexpr int N_COMP = 4, NARROW_PERCENT = 25;
+    bool progressive = false;  // blocks become ready while x is still arriving (banded matrices): narrow launches pay
     int nb = 0, chunks_per_block = 0;
     std::vector<int> colmax, row_end;  // per block: highest column referenced (running max), one past its last row
-    cudaStream_t up = nullptr, comp = nullptr, down = nullptr;
+    cudaStream_t up = nullptr, comp[N_COMP] = {nullptr, nullptr, nullptr, nullptr}, down = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_comp;
     cudaEvent_t ev_start = nullptr;
 };
@@ -1211,7 +1210,7 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
         hp->row_end[hp->nb - 1] = h->rows;
         hp->progressive = hp->nb >= 4 && (long long)hp->colmax[hp->nb / 2] + 1 < (long long)h->cols * 9 / 10;
         G4S_CUDA(cudaStreamCreateWithFlags(&hp->up, cudaStreamNonBlocking));
-        G4S_CUDA(cudaStreamCreateWithFlags(&hp->comp, cudaStreamNonBlocking));
+        for (auto &c : hp->comp) G4S_CUDA(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
         G4S_CUDA(cudaStreamCreateWithFlags(&hp->down, cudaStreamNonBlocking));
         hp->ev_up.resize(hp->nb);
         hp->ev_comp.resize(hp->nb);
@@ -1226,7 +1225,7 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
     // order after whatever the caller queued on the default stream
     G4S_CUDA(cudaEventRecord(hp->ev_start, 0));
     G4S_CUDA(cudaStreamWaitEvent(hp->up, hp->ev_start, 0));
-    G4S_CUDA(cudaStreamWaitEvent(hp->comp, hp->ev_start, 0));
+    for (auto c : hp->comp) G4S_CUDA(cudaStreamWaitEvent(c, hp->ev_start, 0));
     G4S_CUDA(cudaStreamWaitEvent(hp->down, hp->ev_start, 0));
     const bool defer_download = p.n_long > 0;  // the long-row fix-up touches y after every block has run
     long long uploaded = 0;
@@ -1242,13 +1241,12 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
         tr.push_back(e);
     };
     mark(hp->up);
-    static const int fixed_pct = [] {  // G4S_SPMV_HOST_GRID_PERCENT: fixes the share instead of trying
+    static const int narrow_pct = [] {  // G4S_SPMV_HOST_GRID_PERCENT: share of the grid per row-block launch (100: full width)
         const char *e = getenv("G4S_SPMV_HOST_GRID_PERCENT");
-        return e && atoi(e) > 0 ? std::min(100, atoi(e)) : 0;
+        return e && atoi(e) > 0 ? std::min(100, atoi(e)) : HostPipe::NARROW_PERCENT;
     }();
-    const bool trying = hp->progressive && !fixed_pct && hp->calls < 2 * HostPipe::N_TRY;
-    const int call_pct = fixed_pct ? fixed_pct : (trying ? hp->try_pct[hp->calls % HostPipe::N_TRY] : hp->pct);
-    const auto t_call = std::chrono::steady_clock::now();
+    // the long-row fix-up runs after every block: those matrices keep one compute stream (and are not banded anyway)
+    const bool narrow = hp->progressive && !defer_download && narrow_pct < 100;
     for (int b = 0; b < hp->nb; ++b) {
         const long long need = std::min<long long>((long long)hp->colmax[b] + 1, h->cols);
         if (need > uploaded) {
@@ -1258,14 +1256,15 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
         }
         G4S_CUDA(cudaEventRecord(hp->ev_up[b], hp->up));
         mark(hp->up);
-        G4S_CUDA(cudaStreamWaitEvent(hp->comp, hp->ev_up[b], 0));
+        cudaStream_t comp = hp->comp[narrow ? b % HostPipe::N_COMP : 0];
+        G4S_CUDA(cudaStreamWaitEvent(comp, hp->ev_up[b], 0));
         const int c0 = b * hp->chunks_per_block, c1 = std::min(c0 + hp->chunks_per_block, p.nchunks);
-        t_grid_percent = (hp->progressive && b + 1 < hp->nb) ? call_pct : 0;  // the last block is on the critical path: full speed
-        rc = spmv_run(h, h->x_dev, h->y_dev, nullptr, false, hp->comp, nullptr, c0, c1);
+        t_grid_percent = (narrow && b + 1 < hp->nb) ? narrow_pct : 0;  // the last block is on the critical path: full width
+        rc = spmv_run(h, h->x_dev, h->y_dev, nullptr, false, comp, nullptr, c0, c1);
         t_grid_percent = 0;
         if (rc) return rc;
-        G4S_CUDA(cudaEventRecord(hp->ev_comp[b], hp->comp));
-        mark(hp->comp);
+        G4S_CUDA(cudaEventRecord(hp->ev_comp[b], comp));
+        mark(comp);
         if (!defer_download && hp->row_end[b] > row0) {
             G4S_CUDA(cudaStreamWaitEvent(hp->down, hp->ev_comp[b], 0));
             G4S_CUDA(cudaMemcpyAsync(y + row0, h->y_dev + row0, sizeof(double) * (size_t)(hp->row_end[b] - row0),
@@ -1275,24 +1274,13 @@ int spmv_host_pipelined(g4s_csr *h, const double *x, double *y) {
         mark(hp->down);
     }
     if (defer_download) {
-        spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, hp->comp>>>(p.long_rows, p.n_long, p.carry, nullptr, h->y_dev);
+        spmv_long_fixup_kernel<<<(p.n_long + 127) / 128, 128, 0, hp->comp[0]>>>(p.long_rows, p.n_long, p.carry, nullptr, h->y_dev);
         G4S_CHECK_LAUNCH("spmv_long_fixup_kernel");
-        G4S_CUDA(cudaMemcpyAsync(y, h->y_dev, sizeof(double) * (size_t)h->rows, cudaMemcpyDeviceToHost, hp->comp));
-        G4S_CUDA(cudaStreamSynchronize(hp->comp));
+        G4S_CUDA(cudaMemcpyAsync(y, h->y_dev, sizeof(double) * (size_t)h->rows, cudaMemcpyDeviceToHost, hp->comp[0]));
+        G4S_CUDA(cudaStreamSynchronize(hp->comp[0]));
     }
     G4S_CUDA(cudaStreamSynchronize(hp->down));
-    G4S_CUDA(cudaStreamSynchronize(hp->comp));
-    if (trying) {
-        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
-        double &best = hp->try_best[hp->calls % HostPipe::N_TRY];
-        best = std::min(best, secs);
-        if (++hp->calls == 2 * HostPipe::N_TRY) {
-            int k = 0;
-            for (int q = 1; q < HostPipe::N_TRY; ++q)
-                if (hp->try_best[q] < hp->try_best[k] * 0.98) k = q;  // a narrower grid has to win by 2 %
-            hp->pct = hp->try_pct[k];
-        }
-    }
+    for (auto c : hp->comp) G4S_CUDA(cudaStreamSynchronize(c));
     if (trace) {
         fprintf(stderr, "g4s_spmv_host trace (ms since the first copy was queued): block  upload  product  download\n");
         for (int b = 0; b < hp->nb; ++b) {
@@ -1312,7 +1300,8 @@ void spmv_free_host_pipe(g4s_csr *h) {
     for (auto e : hp->ev_comp) cudaEventDestroy(e);
     if (hp->ev_start) cudaEventDestroy(hp->ev_start);
     if (hp->up) cudaStreamDestroy(hp->up);
-    if (hp->comp) cudaStreamDestroy(hp->comp);
+    for (auto c : hp->comp)
+        if (c) cudaStreamDestroy(c);
     if (hp->down) cudaStreamDestroy(hp->down);
     delete hp;
     h->host_pipe = nullptr;

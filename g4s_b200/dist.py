@@ -305,6 +305,22 @@ class DistSpMV:
         ops.spmv(self.off, self.halo, y_local, main, accumulate=True)
         return y_local
 
+    def apply_host(self, x_host, y_host):
+        """Host-pointer product of the partitioned operator (peer mode), the multi-GPU twin of g4s_spmv_host: x_host / y_host
+        are this rank's slices in PINNED host memory.  x is copied into the shared buffer the product reads; the kernel
+        stores y straight into the pinned buffer (device-mapped under unified addressing: one coalesced 256-byte store per
+        warp and 32 rows), so y travels over the host link WHILE the product runs instead of after it.  Returns when y is
+        complete in host memory."""
+        if self.mode != "peer":
+            raise ValueError("apply_host needs peer mode")
+        if not (x_host.is_pinned() and y_host.is_pinned()):
+            raise ValueError("apply_host needs pinned host tensors")
+        xb = self.next_x()
+        xb.copy_(x_host, non_blocking=True)
+        self.apply(xb, y_host)  # apply() only takes y's address
+        torch.cuda.current_stream().synchronize()
+        return y_host
+
     def _exchange(self, x_local, stream):
         if self.mode == "halo":
             if self.send_idx.numel():
