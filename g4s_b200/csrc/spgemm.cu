@@ -1443,6 +1443,12 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     // ---- row pointers (scan straight into C) + allocation of C's arrays from the stream-ordered pool --------------
     g4s_csr *C = new (std::nothrow) g4s_csr();
     if (!C) return fail(G4S_ERR_ALLOC, "host allocation failed");
+    struct Owner {  // every early return below (G4S_CUDA, G4S_CHECK_LAUNCH, rc) releases C and its arrays
+        g4s_csr *c;
+        ~Owner() {
+            if (c) g4s_csr_destroy(c);
+        }
+    } owner{C};
     C->rows = M;
     C->cols = N;
     C->owns = true;
@@ -1483,7 +1489,6 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     }
     if (rc == G4S_OK && cnnz > 2147483647LL) rc = fail(G4S_ERR_INVALID, "g4s_spgemm: nnz(C) exceeds int32 row pointers");
     if (rc) {
-        g4s_csr_destroy(C);
         return rc;
     }
     C->nnz = cnnz;
@@ -1517,13 +1522,11 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
             G4S_CHECK_LAUNCH("bin_fill_kernel");
         }
         if ((rc = ensure_slabs(bn.count[6]))) {
-            g4s_csr_destroy(C);
             return rc;
         }
     }
     rc = run_phase(a, bn, true, slab_keys, slab_vals, slab_slots, slab_ctas, stream);
     if (rc) {
-        g4s_csr_destroy(C);
         return rc;
     }
     if (phases) G4S_CUDA(cudaEventRecord(ws.ev[4], stream));
@@ -1534,6 +1537,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     if (guess && *ws.hgo != 0) {  // the operands changed under the same handles: forget the guess, multiply again
         guess->stamp = 0;
         g4s_csr_destroy(C);
+        owner.c = nullptr;
         return spgemm_run_impl(A, B, Cout, stream, false);
     }
     for (int i = 0; i < 4; ++i) {
@@ -1577,6 +1581,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     else
         for (auto &gq : t_guess)
             if (gq.matches(A, B, cur_dev)) gq.stamp = ++t_guess_clock;
+    owner.c = nullptr;
     *Cout = C;
     return G4S_OK;
 }
