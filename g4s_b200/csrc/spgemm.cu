@@ -214,19 +214,27 @@ __global__ void bin_fill_kernel(const unsigned char *__restrict__ row_class, int
     if (c > 0) perm[base[c] + wcount[c][w] + my_rank] = i;
 }
 
+// class_count: [NCLASS] histogram, [NCLASS] cursors, then — at MAX_NNZ3_SLOT from the control block's start, passed as
+// max_nnz3 — the longest row of numeric class 3: the warp-per-row kernel's tables are sized by it (launch_numeric_class3)
 __global__ void numeric_class_kernel(const unsigned char *__restrict__ sym_class, const int *__restrict__ row_nnz, int M,
-                                     unsigned char *__restrict__ num_class, int *__restrict__ class_count) {
+                                     unsigned char *__restrict__ num_class, int *__restrict__ class_count,
+                                     int *__restrict__ max_nnz3) {
     __shared__ int hist[NCLASS];
+    __shared__ int m3;
     if (threadIdx.x < NCLASS) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) m3 = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
-        const int c = nnz_class(sym_class[i], row_nnz[i]);
+        const int nz = row_nnz[i];
+        const int c = nnz_class(sym_class[i], nz);
         num_class[i] = (unsigned char)c;
         atomicAdd(&hist[c], 1);
+        if (c == 3 && nz > m3) atomicMax(&m3, nz);
     }
     __syncthreads();
     if (threadIdx.x < NCLASS && hist[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+    if (threadIdx.x == 0 && m3) atomicMax(max_nnz3, m3);
 }
 
 // ---- hash kernels -----------------------------------------------------------------------------------------
@@ -258,6 +266,7 @@ struct SpgemmGuessDev {
     int max_work, merge_lists;
     unsigned long long total_work;
     int ncount[7];
+    int max_nnz3;  // longest row of numeric class 3 (sizes that kernel's tables)
     int check_ncount;
     long long cnnz;
 };
@@ -270,8 +279,10 @@ __global__ void spgemm_validate_bins_kernel(const int *__restrict__ dcount, cons
 __global__ void spgemm_validate_nnz_kernel(const int *__restrict__ dcount2, const int *__restrict__ total,
                                            const SpgemmGuessDev g, int nclass, int *__restrict__ go) {
     bool ok = (long long)*total == g.cnnz;
-    if (g.check_ncount)
+    if (g.check_ncount) {
         for (int c = 0; c < nclass; ++c) ok = ok && dcount2[c] == g.ncount[c];
+        ok = ok && dcount2[2 * nclass + 1] == g.max_nnz3;  // the control block's last word (Workspace::MAX_NNZ3_SLOT)
+    }
     if (!ok) *go = 1;
 }
 
@@ -460,12 +471,26 @@ __global__ void __launch_bounds__(THREADS) spgemm_smem_kernel(const SpgemmArgs a
             // compact the occupied slots
             int *myck = ckeys + g * WMAX;
             double *mycv = cvals + g * WMAX;
-            for (int s = lane; s < tsize; s += GROUP) {
-                const int key = mykeys[s];
-                if (key != -1) {
-                    const int pos = atomicAdd(&cnt[g], 1);
-                    myck[pos] = key;
-                    mycv[pos] = myvals[s];
+            if (GROUP == 32) {  // a warp compacts with ballots: no shared-memory atomics on one counter (tsize is a multiple of 32)
+                int base = 0;
+                for (int s0 = 0; s0 < tsize; s0 += 32) {
+                    const int key = mykeys[s0 + lane];
+                    const unsigned m = __ballot_sync(0xffffffffu, key != -1);
+                    if (key != -1) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        myck[pos] = key;
+                        mycv[pos] = myvals[s0 + lane];
+                    }
+                    base += __popc(m);
+                }
+            } else {
+                for (int s = lane; s < tsize; s += GROUP) {
+                    const int key = mykeys[s];
+                    if (key != -1) {
+                        const int pos = atomicAdd(&cnt[g], 1);
+                        myck[pos] = key;
+                        mycv[pos] = myvals[s];
+                    }
                 }
             }
             group_sync<GROUP>();
@@ -1112,6 +1137,7 @@ struct Bins {
     long long total_work = 0;
     int max_work = 0;
     int merge_lists = MERGE_MAX_A;  // longest row of A in class 1
+    int max_nnz3 = 1 << 30;         // numeric phase: longest row of class 3
     bool fused = false;             // symbolic merge kernel also bins (repeated all-merge-class product)
     MergeFused fz = MergeFused();
 };
@@ -1146,7 +1172,15 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
     // classes spa_from()..6 go through the dense accumulator when the product is narrow enough for the bitmap
     const int first_spa = use_spa(a.N) ? spa_from() : NCLASS;
     if (numeric) {  // tables sized by nnz (load factor <= 1/2 up to the class bound), values + compaction buffers
-        if (first_spa > 3 && (rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream))) return rc;
+        // warp per row: the kernel lives on resident warps (global-load latency of A's row and of the rows of B), and a
+        // warp's table + compaction buffer is what limits them — 9 KB for rows of up to 256 entries, 24 warps per SM.  Sized
+        // by the class's LONGEST row instead: 27-point A*A (125 entries a row) 4.5 KB, 48 warps, numeric 7.42 -> 5.80 ms
+        if (first_spa > 3) {
+            if (b.max_nnz3 <= 64) rc = launch_smem<32, 128, 64, 256, true>(a, list(3), b.count[3], stream);
+            else if (b.max_nnz3 <= 128) rc = launch_smem<32, 256, 128, 256, true>(a, list(3), b.count[3], stream);
+            else rc = launch_smem<32, 512, 256, 256, true>(a, list(3), b.count[3], stream);
+            if (rc) return rc;
+        }
         if (first_spa > 4 && (rc = launch_smem<256, 4096, 2048, 256, true>(a, list(4), b.count[4], stream))) return rc;
         if (first_spa > 5 && (rc = launch_smem<1024, 8192, 8192, 1024, true>(a, list(5), b.count[5], stream))) return rc;
     } else {        // keys only, sized by min(work, cols)
@@ -1173,7 +1207,8 @@ static int run_phase(const SpgemmArgs &a, const Bins &b, bool numeric, int *slab
 // Scratch reused across calls on the calling thread (row work, row lists, counters): SpGEMM is called in loops
 // (the reference's driver runs it 11 times, mm/src/mkl_spgemm.cpp:67-79) and cudaMalloc is a device-wide sync.
 struct Workspace {
-    static constexpr size_t CTL_BYTES = sizeof(unsigned long long) + sizeof(int) * (2 + 4 * NCLASS + 2);
+    static constexpr int MAX_NNZ3_SLOT = 4 * NCLASS + 2;  // index into dcount / hcount
+    static constexpr size_t CTL_BYTES = sizeof(unsigned long long) + sizeof(int) * (2 + 4 * NCLASS + 3);
     int device = -1;
     size_t rows_cap = 0;
     int *row_work = nullptr, *perm = nullptr, *row_nnz = nullptr, *dcount = nullptr;
@@ -1200,7 +1235,7 @@ struct Workspace {
             dgo = reinterpret_cast<int *>(dtotal + 1);
             dcount = dgo + 2;
             G4S_CUDA(cudaMalloc(&spa_next, sizeof(int)));
-            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 2)));
+            G4S_CUDA(cudaMallocHost(&hcount, sizeof(int) * (4 * NCLASS + 3)));
             G4S_CUDA(cudaMallocHost(&htotal, sizeof(unsigned long long)));
             G4S_CUDA(cudaMallocHost(&hgo, sizeof(int)));
             for (auto &e : ev) G4S_CUDA(cudaEventCreate(&e));
@@ -1469,12 +1504,16 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
     // rows of classes 1 and 2 never move; if one of them holds every row there is nothing to re-bin
     const bool rebin = M > 0 && !(b.identity && (b.count[1] == M || b.count[2] == M));
     if (rebin) {
-        numeric_class_kernel<<<blocks, threads, 0, stream>>>(ws.row_class, row_nnz, M, ws.num_class, dcount2);
+        numeric_class_kernel<<<blocks, threads, 0, stream>>>(ws.row_class, row_nnz, M, ws.num_class, dcount2,
+                                                             dcount + Workspace::MAX_NNZ3_SLOT);
         G4S_CHECK_LAUNCH("numeric_class_kernel");
         if (guess) {
             for (int c = 0; c < NCLASS; ++c) ws.hcount[2 * NCLASS + 1 + c] = guess->g.ncount[c];
+            ws.hcount[Workspace::MAX_NNZ3_SLOT] = guess->g.max_nnz3;
         } else {
             G4S_CUDA(cudaMemcpyAsync(ws.hcount + 2 * NCLASS + 1, dcount2, sizeof(int) * NCLASS, cudaMemcpyDeviceToHost, stream));
+            G4S_CUDA(cudaMemcpyAsync(ws.hcount + Workspace::MAX_NNZ3_SLOT, dcount + Workspace::MAX_NNZ3_SLOT, sizeof(int),
+                                     cudaMemcpyDeviceToHost, stream));
         }
     }
     // (Row pointers written by the symbolic merge kernel itself — CTA scan + decoupled look-back over its 256-row blocks,
@@ -1515,6 +1554,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
             if (c && bn.count[c] == M) bn.identity = true;
         }
         bn.offset[NCLASS] = off;
+        bn.max_nnz3 = ws.hcount[Workspace::MAX_NNZ3_SLOT];
         bn.perm = ws.perm2;
         if (!bn.identity) {
             G4S_CUDA(cudaMemcpyAsync(dcount2 + NCLASS, cur2, sizeof(cur2), cudaMemcpyHostToDevice, stream));
@@ -1573,6 +1613,7 @@ static int spgemm_run_impl(g4s_csr *A, g4s_csr *B, g4s_csr **Cout, cudaStream_t 
         slot->g.max_work = (int)b.max_work;
         slot->g.merge_lists = b.merge_lists;
         slot->g.total_work = (unsigned long long)b.total_work;
+        slot->g.max_nnz3 = rebin ? bn.max_nnz3 : 0;
         slot->g.check_ncount = rebin ? 1 : 0;
         slot->g.cnnz = cnnz;
         slot->rebin = rebin;

@@ -71,7 +71,8 @@ CASES = {
     "rand_rect": lambda: (random_csr(120, 200, 0.05, 2, empty_rows=True),
                           random_csr(200, 90, 0.04, 3, empty_rows=True)),              # class 0-2
     "rand_dense_rows": lambda: (random_csr(64, 64, 0.6, 4), random_csr(64, 64, 0.6, 5)),  # w capped by cols
-    "banded_20": lambda: (banded(600, 20, 6),) * 2,                                    # work 1681: class 3
+    "banded_10": lambda: (banded(900, 10, 16),) * 2,                                   # work 441, <= 41 a row: class 3, 128-slot tables
+    "banded_20": lambda: (banded(600, 20, 6),) * 2,                                    # work 1681, <= 81 a row: class 3, 256-slot tables
     "banded_35": lambda: (banded(5000, 35, 7),) * 2,                                   # work 5041, cols 5000: class 4
     "powerlaw_hub": lambda: (powerlaw_csr(12000, 7, max_deg=6000),) * 2,               # class 5
     "powerlaw_big_hub": lambda: (powerlaw_csr(24000, 9, max_deg=2500),) * 2,           # class 6 (dense accumulator; long B rows)
