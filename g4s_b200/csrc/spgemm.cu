@@ -982,6 +982,7 @@ __global__ void __launch_bounds__(1024) spgemm_global_kernel(const SpgemmArgs a,
 // rows of B longer than SPA_LONG_B are walked by the whole CTA instead of one lane group.
 constexpr int SPA_MAX_COLS = 1 << 20;   // 128 KB of bitmap
 constexpr int SPA_LONG_B = 2048;
+constexpr int SPA_BATCH = 1024;  // entries of A's row staged per step = threads per CTA
 template <bool NUMERIC>
 __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, const int *__restrict__ list, int nlist,
                                                            double *__restrict__ slabs, int nwords,
@@ -990,6 +991,9 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
     extern __shared__ unsigned spa_sm[];
     unsigned *bm = spa_sm;                 // [nwords] one bit per column of C
     int *wsum = reinterpret_cast<int *>(spa_sm + nwords);  // [32] per-warp counts, [32] = total, [33] = row index
+    double *s_av = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(spa_sm) +
+                                              ((sizeof(unsigned) * ((size_t)nwords + 34) + 15) & ~(size_t)15));  // [SPA_BATCH]
+    int *s_bs = reinterpret_cast<int *>(s_av + SPA_BATCH), *s_be = s_bs + SPA_BATCH;                           // [SPA_BATCH] each
     constexpr unsigned FULL = 0xffffffffu;
     double *dense = slabs + (size_t)blockIdx.x * a.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1007,29 +1011,48 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
         if (idx >= nlist) break;
         const int row = list ? list[idx] : idx;
         const int as = a.arpt[row], ae = a.arpt[row + 1];
-        // short rows of B: one lane group each
-        for (int j = as + my_sub; j < ae; j += nsub) {
-            const int k = a.acol[j];
-            const int bs = a.brpt[k], be = a.brpt[k + 1];
-            if (be - bs >= SPA_LONG_B) continue;
-            const double av = NUMERIC ? a.aval[j] : 0.0;
-            for (int p = bs + sl; p < be; p += SUB) {
-                const int col = __ldg(a.bcol + p);
-                atomicOr(&bm[col >> 5], 1u << (col & 31));
-                if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+        // A's row is taken 1024 entries at a time: every thread fetches ONE entry — its column, the extent of the row of B it
+        // selects, its value — into shared memory, so the dependent chain acol -> brpt is paid once per batch with 1024 loads
+        // in flight instead of once per entry by the lane group that owns it (ncu: this kernel waits on loads, 52 of 100
+        // cycles per issue; a lane group's chain was acol -> brpt -> bcol/bval -> red).
+        for (int base = as; base < ae; base += SPA_BATCH) {
+            const int jj = base + (int)threadIdx.x;
+            int bs_t = 0, be_t = 0;
+            if (jj < ae) {
+                const int k = __ldg(a.acol + jj);
+                bs_t = __ldg(a.brpt + k);
+                be_t = __ldg(a.brpt + k + 1);
+                if (NUMERIC) s_av[threadIdx.x] = __ldg(a.aval + jj);
             }
-        }
-        // long rows of B: the whole CTA
-        for (int j = as; j < ae; ++j) {
-            const int k = a.acol[j];
-            const int bs = a.brpt[k], be = a.brpt[k + 1];
-            if (be - bs < SPA_LONG_B) continue;
-            const double av = NUMERIC ? a.aval[j] : 0.0;
-            for (int p = bs + threadIdx.x; p < be; p += blockDim.x) {
-                const int col = __ldg(a.bcol + p);
-                atomicOr(&bm[col >> 5], 1u << (col & 31));
-                if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+            s_bs[threadIdx.x] = bs_t;
+            s_be[threadIdx.x] = be_t;
+            const int any_long = __syncthreads_or(be_t - bs_t >= SPA_LONG_B);
+            const int nb = min(SPA_BATCH, ae - base);
+            // short rows of B: one lane group each
+            for (int e = my_sub; e < nb; e += nsub) {
+                const int bs = s_bs[e], be = s_be[e];
+                if (be - bs >= SPA_LONG_B) continue;
+                const double av = NUMERIC ? s_av[e] : 0.0;
+                for (int p = bs + sl; p < be; p += SUB) {
+                    const int col = __ldg(a.bcol + p);
+                    atomicOr(&bm[col >> 5], 1u << (col & 31));
+                    if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+                }
             }
+            // long rows of B: the whole CTA
+            if (any_long) {
+                for (int e = 0; e < nb; ++e) {
+                    const int bs = s_bs[e], be = s_be[e];
+                    if (be - bs < SPA_LONG_B) continue;
+                    const double av = NUMERIC ? s_av[e] : 0.0;
+                    for (int p = bs + threadIdx.x; p < be; p += blockDim.x) {
+                        const int col = __ldg(a.bcol + p);
+                        atomicOr(&bm[col >> 5], 1u << (col & 31));
+                        if (NUMERIC) atomicAdd(&dense[col], av * __ldg(a.bval + p));
+                    }
+                }
+            }
+            __syncthreads();  // the batch arrays are rewritten by the next step
         }
         if (NUMERIC) __threadfence();  // the accumulators are read back by other threads below
         __syncthreads();
@@ -1070,16 +1093,27 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
                 const int up = __shfl_up_sync(FULL, inc, o);
                 if (lane >= o) inc += up;
             }
-            int pos = running + inc - cnt;
-            running += __shfl_sync(FULL, inc, 31);
-            while (bits) {
-                const int col = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                a.ccol[pos] = col;
-                a.cval[pos] = __ldcg(dense + col);
-                dense[col] = 0.0;
-                ++pos;
+            // Output o of this batch of 32 words goes to lane o & 31: neighbouring lanes then handle neighbouring columns, so
+            // the stores to C are coalesced and the accumulator reads / resets of an instruction share sectors.  (One lane
+            // emitting its own word's bits made every access of the row's 4 per entry a transaction of its own — and the
+            // kernel's L2 transactions, 1.05 G on R-MAT 16 against 401 M products, are what bounds it.)
+            const int total = __shfl_sync(FULL, inc, 31);
+            for (int ob = 0; ob < total; ob += 32) {  // warp-uniform trip count
+                const int o = min(ob + lane, total - 1);
+                int owner = 0;  // first lane whose inclusive count exceeds o
+#pragma unroll
+                for (int step = 16; step; step >>= 1)
+                    if (__shfl_sync(FULL, inc, owner + step - 1) <= o) owner += step;
+                const int nth = o - (__shfl_sync(FULL, inc, owner) - __shfl_sync(FULL, cnt, owner));
+                const unsigned obits = __shfl_sync(FULL, bits, owner);
+                const int col = ((wb + owner) << 5) + (int)__fns(obits, 0, nth + 1);
+                if (ob + lane < total) {
+                    a.ccol[running + o] = col;
+                    a.cval[running + o] = __ldcg(dense + col);
+                    dense[col] = 0.0;
+                }
             }
+            running += total;
         }
         __threadfence();  // the zeros must be in place before the next row's red.add
     }
@@ -1309,18 +1343,22 @@ static int spa_from() {
 }
 // CTAs of the dense-accumulator kernel: two per SM when the bitmap allows.  Capping the grid so that all fp64 slabs fit
 // L2 (96 MB) was measured and is worse (R-MAT 18: 100 -> 305 ms): the parallelism is worth more than the spill to DRAM.
+// bitmap + counters (rounded to 16 bytes) + one batch of A's row: extents of the selected rows of B and A's values
+static size_t spa_smem_bytes(int cols) {
+    return ((sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34) + 15) & ~(size_t)15) + SPA_BATCH * (2 * sizeof(int) + sizeof(double));
+}
 static int spa_grid(int cols, int rows_in_class) {
-    const size_t smem = sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34);
+    const size_t smem = spa_smem_bytes(cols);
     const int per_sm = smem <= 100 * 1024 ? 2 : 1;
     return std::max(1, std::min(rows_in_class, sm_count() * per_sm));
 }
 static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
     Workspace &ws = t_ws;
     const int nwords = (a.N + 31) / 32;
-    const size_t smem = sizeof(unsigned) * ((size_t)nwords + 34);
+    const size_t smem = spa_smem_bytes(a.N);
     static PerDeviceOnce configured;
     if (configured.needs()) {
-        const int cap = (int)(sizeof(unsigned) * (SPA_MAX_COLS / 32 + 34));
+        const int cap = (int)spa_smem_bytes(SPA_MAX_COLS);
         G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         configured.done();
