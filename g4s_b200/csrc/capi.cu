@@ -54,6 +54,7 @@ struct XParts;
 int spmv_run(g4s_csr *h, const double *x, double *y, const int *row_map, bool accum, cudaStream_t stream,
              const XParts *parts = nullptr, int chunk_begin = 0, int chunk_end = -1);
 int spmv_host_pipelined(g4s_csr *h, const double *x, double *y);
+int exclusive_scan_i32(const int *in, int *out, long long n, int write_total, long long *total_host, cudaStream_t stream);
 void spmv_free_host_pipe(g4s_csr *h);
 int spmv_run_partitioned(g4s_csr *h, int world, int self, const double *const *x_parts, const int *cuts, double *y,
                          const unsigned long long *flags, unsigned long long epoch,
@@ -204,6 +205,16 @@ extern "C" {
 const char *g4s_last_error(void) { return t_error.c_str(); }
 const char *g4s_version(void) { return "g4s_b200 0.1 (sm_100a)"; }
 long long g4s_kernel_launch_count(void) { return g_launches.load(); }
+
+// scan(in, out, N) of the reference (mm/inc/utility.h:166-209) on device arrays; the implementation lives in spmv.cu
+int g4s_exclusive_scan_i32_device(const int *in_dev, int *out_dev, long long n, int write_total, long long *total_host,
+                                  void *stream) {
+    if (n < 0 || (n > 0 && (!in_dev || !out_dev)) || (write_total && !out_dev))
+        return fail(G4S_ERR_INVALID, "g4s_exclusive_scan_i32_device: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    return exclusive_scan_i32(in_dev, out_dev, n, write_total, total_host, (cudaStream_t)stream);
+}
 
 int g4s_device_count(void) {
     int n = 0;

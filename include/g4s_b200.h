@@ -364,6 +364,14 @@ int g4s_ebe_matvec_device(int nel, int ndof, const double *elt_k_dev, const int 
 int g4s_radix_sort_pairs_device(unsigned long long *keys_dev, unsigned long long *keys_tmp_dev, void *values_dev,
                                 void *values_tmp_dev, long long n, int key_bits, void *stream);
 
+/* Exclusive prefix sum of n int32 counts on the device: out[k] = in[0] + ... + in[k-1], and out[n] = the total when
+ * write_total is non-zero (out then has n + 1 entries); out may alias in.  The reference's scan(in, out, N)
+ * (mm/inc/utility.h:166-209), as hash_symbolic calls it to turn row_nz into C's row pointers (mm/inc/hash_mult.h:506-507).
+ * Three launches (tile sums, their scan, apply) over 2048-entry tiles.  *total_host, when non-NULL, receives the 64-bit total and the call
+ * synchronises `stream`; the int32 outputs are only meaningful while the total fits. */
+int g4s_exclusive_scan_i32_device(const int *in_dev, int *out_dev, long long n, int write_total, long long *total_host,
+                                  void *stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * OptMatmul: the dense fp64 product DeePMD-kit routes through the G4S engine,
  * res[M,K] = xx[M,N] w[N,K], all row-major (deepmd/source/op/opt_matmul.cc:24-62; engine loop

@@ -116,6 +116,35 @@ def test_spmv_on_rmat_matches_oracle(g4s, oracle):
     assert np.all(np.abs(y - want) <= 1e-12 * scale + 1e-300)
 
 
+@pytest.mark.parametrize("n", [0, 1, 5, 2047, 2048, 2049, 131072, 1000003, (1 << 22) + 1])
+def test_exclusive_scan_matches_reference_scan(g4s, n):
+    """The reference's scan(in, out, N) (mm/inc/utility.h:166-209: out[0] = 0, out[k] = out[k-1] + in[k-1]; parallel above
+    2^17 entries) on the device: tile boundaries (2048 entries a tile), one tile, thousands of tiles, in place, with and
+    without the trailing total, twice in a row, and a smaller scan after a larger one (the scratch is kept between calls)."""
+    import ctypes as C
+
+    import torch
+
+    L = g4s.lib()
+    L.g4s_exclusive_scan_i32_device.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(n)
+    for rep in range(2):
+        a = rng.integers(0, 40, n).astype(np.int32)
+        want = np.concatenate(([0], np.cumsum(a, dtype=np.int64)))
+        d_in = torch.from_numpy(a).cuda()
+        d_out = torch.full((n + 1,), -7, dtype=torch.int32, device="cuda")
+        total = C.c_longlong(-1)
+        g4s._lib.check(L.g4s_exclusive_scan_i32_device(d_in.data_ptr(), d_out.data_ptr(), n, 1, C.byref(total), None))
+        assert total.value == int(want[-1])
+        assert np.array_equal(d_out.cpu().numpy().astype(np.int64), want)
+        # in place, without the total: entry n stays untouched
+        buf = torch.cat([d_in, torch.full((1,), -7, dtype=torch.int32, device="cuda")])
+        g4s._lib.check(L.g4s_exclusive_scan_i32_device(buf.data_ptr(), buf.data_ptr(), n, 0, None, None))
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got[:n], want[:n]) and got[n] == -7
+
+
 # ---------------------------------------------------------------- BSR SpMM ------------------------------------------
 def bsr_case(mb, density, bs, seed):
     rng = np.random.default_rng(seed)
