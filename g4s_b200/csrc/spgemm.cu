@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
         // selects, its value — into shared memory, so the dependent chain acol -> brpt is paid once per batch with 1024 loads
         // in flight instead of once per entry by the lane group that owns it (ncu: this kernel waits on loads, 52 of 100
         // cycles per issue; a lane group's chain was acol -> brpt -> bcol/bval -> red).
-        for (int base = as; base < ae; base += SPA_BATCH) {
+        for (int base = as; base < ae; base += (int)blockDim.x) {
             const int jj = base + (int)threadIdx.x;
             int bs_t = 0, be_t = 0;
             if (jj < ae) {
@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(1024) spgemm_spa_kernel(const SpgemmArgs a, co
             s_bs[threadIdx.x] = bs_t;
             s_be[threadIdx.x] = be_t;
             const int any_long = __syncthreads_or(be_t - bs_t >= SPA_LONG_B);
-            const int nb = min(SPA_BATCH, ae - base);
+            const int nb = min((int)blockDim.x, ae - base);
             // short rows of B: one lane group each
             for (int e = my_sub; e < nb; e += nsub) {
                 const int bs = s_bs[e], be = s_be[e];
@@ -1347,9 +1347,19 @@ static int spa_from() {
 static size_t spa_smem_bytes(int cols) {
     return ((sizeof(unsigned) * ((size_t)(cols + 31) / 32 + 34) + 15) & ~(size_t)15) + SPA_BATCH * (2 * sizeof(int) + sizeof(double));
 }
-static int spa_grid(int cols, int rows_in_class) {
+// Threads per CTA of the dense-accumulator kernel.  Numeric: 1024 (two CTAs per SM) — every CTA owns an fp64 slab of N columns
+// that has to live in L2, and more, smaller CTAs spill more of them (R-MAT 16 / 18 numeric: 8.9 / 81 ms at 1024 threads,
+// 10.1 / 113 ms at 512, 14.5 / 121 ms at 256).  Symbolic: 512 (four CTAs per SM) — it has only its bitmap, and its barriers
+// around every row cost less with fewer warps behind them (2.23 / 8.04 -> 1.89 / 6.44 ms).  G4S_SPGEMM_SPA_THREADS overrides both.
+static int spa_threads(bool numeric) {
+    const char *e = getenv("G4S_SPGEMM_SPA_THREADS");
+    const int v = e ? atoi(e) : (numeric ? 1024 : 512);
+    return v == 256 || v == 512 ? v : 1024;
+}
+static int spa_grid(int cols, int rows_in_class, bool numeric) {
     const size_t smem = spa_smem_bytes(cols);
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int by_smem = (int)std::max<size_t>(1, (200 * 1024) / smem), by_threads = 2048 / spa_threads(numeric);
+    const int per_sm = std::min(by_smem, by_threads);
     return std::max(1, std::min(rows_in_class, sm_count() * per_sm));
 }
 static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool numeric, cudaStream_t stream) {
@@ -1363,12 +1373,12 @@ static int launch_spa(const SpgemmArgs &a, const int *list, int nlist, bool nume
         G4S_CUDA(cudaFuncSetAttribute(spgemm_spa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         configured.done();
     }
-    const int grid = spa_grid(a.N, nlist);
-    int rc = ws.ensure_spa((size_t)grid * a.N, stream);
+    const int grid = spa_grid(a.N, nlist, numeric);
+    int rc = ws.ensure_spa((size_t)spa_grid(a.N, 1 << 30, true) * a.N, stream);
     if (rc) return rc;
     G4S_CUDA(cudaMemsetAsync(ws.spa_next, 0, sizeof(int), stream));
-    if (numeric) spgemm_spa_kernel<true><<<grid, 1024, smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
-    else spgemm_spa_kernel<false><<<grid, 1024, smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
+    if (numeric) spgemm_spa_kernel<true><<<grid, spa_threads(true), smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
+    else spgemm_spa_kernel<false><<<grid, spa_threads(false), smem, stream>>>(a, list, nlist, ws.spa_dense, nwords, ws.spa_next);
     G4S_CHECK_LAUNCH("spgemm_spa_kernel");
     return G4S_OK;
 }
